@@ -1,0 +1,59 @@
+"""ctypes binding of libepnet_b200.so -- the only door from Python into the CUDA kernels.
+
+There is deliberately no fallback: if the library is missing and cannot be built, importing raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes, exactly the declarations of include/epnet_b200.h
+SIGNATURES = {
+    "epnet_furthest_point_sampling": [_c_int] * 3 + [_c_void_p] * 4,
+    "epnet_gather_points": [_c_int] * 4 + [_c_void_p] * 4,
+    "epnet_gather_points_grad": [_c_int] * 4 + [_c_void_p] * 4,
+    "epnet_ball_query": [_c_int] * 3 + [_c_float, _c_int] + [_c_void_p] * 4,
+    "epnet_group_points": [_c_int] * 5 + [_c_void_p] * 4,
+    "epnet_group_points_grad": [_c_int] * 5 + [_c_void_p] * 4,
+    "epnet_three_nn": [_c_int] * 3 + [_c_void_p] * 5,
+    "epnet_three_interpolate": [_c_int] * 4 + [_c_void_p] * 5,
+    "epnet_three_interpolate_grad": [_c_int] * 4 + [_c_void_p] * 5,
+    "epnet_grid_gather_bilinear": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
+    "epnet_grid_gather_bilinear_grad": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
+}
+
+
+def _load():
+    path = _build.LIB
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception as exc:  # noqa: BLE001 - re-raised below when the library is unusable
+            if not os.path.exists(path):
+                raise ImportError(
+                    "epnet_b200: libepnet_b200.so is missing and could not be built (%s). "
+                    "Run `python -m epnet_b200.build` where nvcc is available." % exc)
+    lib = ctypes.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _c_int
+    lib.epnet_abi_version.restype = _c_int
+    lib.epnet_error_string.argtypes = [_c_int]
+    lib.epnet_error_string.restype = ctypes.c_char_p
+    return lib
+
+
+LIB = _load()
+LIB_PATH = _build.LIB
+
+
+class EpnetKernelError(RuntimeError):
+    pass
+
+
+def check(code, what):
+    if code != 0:
+        raise EpnetKernelError("%s failed: %s" % (what, LIB.epnet_error_string(code).decode()))

@@ -1,0 +1,123 @@
+// LI-Fusion point-wise image-feature gather for B200.  Replaces the torch.nn.functional.grid_sample
+// call in Feature_Gather (/root/reference/lib/net/pointnet2_msg.py:107-120): bilinear interpolation,
+// zero padding, grid of shape (B,1,N,2) -- i.e. one row of N sample points per scene.
+//
+// ATen's generic grid_sampler_2d recomputes the four tap addresses and weights for every (point,
+// channel) pair.  Here a thread owns one point: tap offsets/weights are computed once and reused for
+// kGgChannels channel planes; the per-channel work is 4 L2 gathers, 4 FMAs and one store that is
+// coalesced across the warp (consecutive threads = consecutive points of the (B,C,N) output).
+// Arithmetic follows ATen (unnormalise, floor, weights as products of corner distances, taps added in
+// the order nw, ne, sw, se); results agree with grid_sample to ~1e-7, the test tolerance is 1e-5.
+#include "common.cuh"
+
+namespace epnet {
+
+constexpr int kGgThreads = 128;
+constexpr int kGgChannels = 16;
+
+struct Taps {
+    int o[4];    // plane offsets (clamped to 0 when the tap is outside; its weight is then 0)
+    float w[4];  // nw, ne, sw, se
+};
+
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int align_corners)
+{
+    float ix, iy;
+    if (align_corners) {
+        ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
+        iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+    } else {
+        ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
+        iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+    }
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx, wy1 = iy - fy;           // distance to the west / north corner
+    const float wx0 = (float)x1 - ix, wy0 = (float)y1 - iy;
+    const bool xin0 = x0 >= 0 && x0 < w, xin1 = x1 >= 0 && x1 < w;
+    const bool yin0 = y0 >= 0 && y0 < h, yin1 = y1 >= 0 && y1 < h;
+    Taps t;
+    t.w[0] = (xin0 && yin0) ? wx0 * wy0 : 0.f;
+    t.w[1] = (xin1 && yin0) ? wx1 * wy0 : 0.f;
+    t.w[2] = (xin0 && yin1) ? wx0 * wy1 : 0.f;
+    t.w[3] = (xin1 && yin1) ? wx1 * wy1 : 0.f;
+    t.o[0] = (xin0 && yin0) ? y0 * w + x0 : 0;
+    t.o[1] = (xin1 && yin0) ? y0 * w + x1 : 0;
+    t.o[2] = (xin0 && yin1) ? y1 * w + x0 : 0;
+    t.o[3] = (xin1 && yin1) ? y1 * w + x1 : 0;
+    return t;
+}
+
+__global__ void __launch_bounds__(kGgThreads)
+grid_gather_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, const float *__restrict__ xy, int align_corners,
+                   float *__restrict__ out)
+{
+    const int scene = blockIdx.z;
+    const int i = blockIdx.x * kGgThreads + threadIdx.x;
+    if (i >= n) return;
+    const size_t plane = (size_t)h * w;
+    fmap += (size_t)scene * c * plane;
+    out += (size_t)scene * c * n;
+    const float2 g = __ldg(reinterpret_cast<const float2 *>(xy + ((size_t)scene * n + i) * 2));
+    const Taps t = make_taps(g.x, g.y, h, w, align_corners);
+    const int c_begin = blockIdx.y * kGgChannels;
+    const int c_end = min(c, c_begin + kGgChannels);
+#pragma unroll 4
+    for (int ch = c_begin; ch < c_end; ++ch) {
+        const float *p = fmap + (size_t)ch * plane;
+        float acc = __ldg(p + t.o[0]) * t.w[0];
+        acc += __ldg(p + t.o[1]) * t.w[1];
+        acc += __ldg(p + t.o[2]) * t.w[2];
+        acc += __ldg(p + t.o[3]) * t.w[3];
+        out[(size_t)ch * n + i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kGgThreads)
+grid_gather_grad_kernel(int c, int h, int w, int n, const float *__restrict__ grad_out, const float *__restrict__ xy,
+                        int align_corners, float *__restrict__ grad_fmap)
+{
+    const int scene = blockIdx.z;
+    const int i = blockIdx.x * kGgThreads + threadIdx.x;
+    if (i >= n) return;
+    const size_t plane = (size_t)h * w;
+    grad_fmap += (size_t)scene * c * plane;
+    grad_out += (size_t)scene * c * n;
+    const float2 g = __ldg(reinterpret_cast<const float2 *>(xy + ((size_t)scene * n + i) * 2));
+    const Taps t = make_taps(g.x, g.y, h, w, align_corners);
+    const int c_begin = blockIdx.y * kGgChannels;
+    const int c_end = min(c, c_begin + kGgChannels);
+    for (int ch = c_begin; ch < c_end; ++ch) {
+        float *p = grad_fmap + (size_t)ch * plane;
+        const float go = __ldg(grad_out + (size_t)ch * n + i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t.w[k] != 0.f) atomicAdd(p + t.o[k], go * t.w[k]);
+    }
+}
+
+}  // namespace epnet
+
+EPNET_API int epnet_grid_gather_bilinear(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners,
+                                         float *out, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c < 0 || h <= 0 || w <= 0 || n < 0 || !fmap || !xy || !out) return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(xy) & 7) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0 || c == 0 || n == 0) return EPNET_OK;
+    dim3 grid((n + kGgThreads - 1) / kGgThreads, (c + kGgChannels - 1) / kGgChannels, b);
+    grid_gather_kernel<<<grid, kGgThreads, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_grid_gather_bilinear_grad(int b, int c, int h, int w, int n, const float *grad_out, const float *xy,
+                                              int align_corners, float *grad_fmap, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c < 0 || h <= 0 || w <= 0 || n < 0 || !grad_out || !xy || !grad_fmap) return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(xy) & 7) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0 || c == 0 || n == 0) return EPNET_OK;
+    dim3 grid((n + kGgThreads - 1) / kGgThreads, (c + kGgChannels - 1) / kGgChannels, b);
+    grid_gather_grad_kernel<<<grid, kGgThreads, 0, (cudaStream_t)stream>>>(c, h, w, n, grad_out, xy, align_corners, grad_fmap);
+    EPNET_RETURN_LAUNCH_STATUS();
+}

@@ -1,0 +1,218 @@
+"""EPNet's two-stream RPN backbone (PointNet++ MSG point stream + image stream + LI-Fusion), mirroring
+/root/reference/lib/net/pointnet2_msg.py: same class and attribute names (so state dicts interchange),
+same forward signature and return values.  The point ops and the LI-Fusion gather run on the B200
+kernels; the dense image convolutions stay with cuDNN, as SURVEY.md section 8 scopes them.
+
+Instead of the reference's process-global `cfg` (lib/config.py) the network is described by a
+BackboneConfig whose defaults are the published LI_Fusion_with_attention_use_ce_loss.yaml values;
+`BackboneConfig.from_cfg(cfg)` reads a reference-style cfg object.
+"""
+from dataclasses import dataclass, field
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import li_fusion
+from . import pointnet2_utils
+from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+
+
+@dataclass
+class BackboneConfig:
+    # lib/config.py:68-78 (RPN.*), tools/cfgs/LI_Fusion_with_attention_use_ce_loss.yaml:43,56-64
+    input_channels: int = 0  # RPN.USE_INTENSITY False -> xyz only (lib/net/rpn.py:19)
+    use_xyz: bool = True
+    use_bn: bool = True
+    npoints: List[int] = field(default_factory=lambda: [4096, 1024, 256, 64])
+    radius: List[List[float]] = field(default_factory=lambda: [[0.1, 0.5], [0.5, 1.0], [1.0, 2.0], [2.0, 4.0]])
+    nsample: List[List[int]] = field(default_factory=lambda: [[16, 32], [16, 32], [16, 32], [16, 32]])
+    mlps: List[List[List[int]]] = field(default_factory=lambda: [[[16, 16, 32], [32, 32, 64]],
+                                                                [[64, 64, 128], [64, 96, 128]],
+                                                                [[128, 196, 256], [128, 196, 256]],
+                                                                [[256, 256, 512], [256, 384, 512]]])
+    fp_mlps: List[List[int]] = field(default_factory=lambda: [[128, 128], [256, 256], [512, 512], [512, 512]])
+    # lib/config.py:36-45 (LI_FUSION.*), yaml:24-27
+    li_fusion: bool = True
+    image_attention: bool = True
+    img_features_channel: int = 128
+    img_channels: List[int] = field(default_factory=lambda: [3, 64, 128, 256, 512])
+    point_channels: List[int] = field(default_factory=lambda: [96, 256, 512, 1024])
+    deconv_reduce: List[int] = field(default_factory=lambda: [16, 16, 16, 16])
+    deconv_kernels: List[int] = field(default_factory=lambda: [2, 4, 8, 16])
+    image_size: List[float] = field(default_factory=lambda: [1280.0, 384.0])  # pointnet2_msg.py:208
+    # torch >= 1.3 evaluates the reference's unchanged grid_sample call with align_corners=False
+    align_corners: bool = False
+
+    @classmethod
+    def from_cfg(cls, cfg, input_channels=None, use_xyz=True):
+        rpn, li = cfg.RPN, cfg.LI_FUSION
+        if input_channels is None:
+            input_channels = int(rpn.USE_INTENSITY) + 3 * int(rpn.USE_RGB)
+        return cls(input_channels=input_channels, use_xyz=use_xyz, use_bn=rpn.USE_BN,
+                   npoints=list(rpn.SA_CONFIG.NPOINTS), radius=[list(r) for r in rpn.SA_CONFIG.RADIUS],
+                   nsample=[list(s) for s in rpn.SA_CONFIG.NSAMPLE],
+                   mlps=[[list(m) for m in level] for level in rpn.SA_CONFIG.MLPS],
+                   fp_mlps=[list(m) for m in rpn.FP_MLPS], li_fusion=li.ENABLED,
+                   image_attention=li.ADD_Image_Attention, img_features_channel=li.IMG_FEATURES_CHANNEL,
+                   img_channels=list(li.IMG_CHANNELS), point_channels=list(li.POINT_CHANNELS),
+                   deconv_reduce=list(li.DeConv_Reduce), deconv_kernels=list(li.DeConv_Kernels))
+
+
+class BasicBlock(nn.Module):
+    """Image-stream stage (pointnet2_msg.py:17-33): conv3x3 -> BN -> ReLU -> conv3x3 with stride 2."""
+
+    def __init__(self, inplanes, outplanes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, outplanes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(outplanes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(outplanes, outplanes, kernel_size=3, stride=2 * stride, padding=1, bias=False)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.bn1(self.conv1(x))))
+
+
+class Fusion_Conv(nn.Module):
+    """Plain LI-Fusion: concat + 1x1 conv + BN + ReLU (pointnet2_msg.py:35-49)."""
+
+    def __init__(self, inplanes, outplanes):
+        super().__init__()
+        self.conv1 = nn.Conv1d(inplanes, outplanes, 1)
+        self.bn1 = nn.BatchNorm1d(outplanes)
+
+    def forward(self, point_features, img_features):
+        return F.relu(self.bn1(self.conv1(torch.cat([point_features, img_features], dim=1))))
+
+
+class IA_Layer(nn.Module):
+    """Point-guided attention over the gathered image features (pointnet2_msg.py:52-81)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.ic, self.pc = channels
+        rc = self.pc // 4
+        self.conv1 = nn.Sequential(nn.Conv1d(self.ic, self.pc, 1), nn.BatchNorm1d(self.pc), nn.ReLU())
+        self.fc1 = nn.Linear(self.ic, rc)
+        self.fc2 = nn.Linear(self.pc, rc)
+        self.fc3 = nn.Linear(rc, 1)
+
+    def forward(self, img_feas, point_feas):
+        batch = img_feas.size(0)
+        img_rows = img_feas.transpose(1, 2).contiguous().view(-1, self.ic)  # (B*N, ic)
+        point_rows = point_feas.transpose(1, 2).contiguous().view(-1, self.pc)  # (B*N, pc)
+        att = torch.sigmoid(self.fc3(torch.tanh(self.fc1(img_rows) + self.fc2(point_rows))))  # (B*N, 1)
+        att = att.squeeze(1).view(batch, 1, -1)
+        return self.conv1(img_feas) * att
+
+
+class Atten_Fusion_Conv(nn.Module):
+    """LI-Fusion with image attention (pointnet2_msg.py:84-104)."""
+
+    def __init__(self, inplanes_I, inplanes_P, outplanes):
+        super().__init__()
+        self.IA_Layer = IA_Layer(channels=[inplanes_I, inplanes_P])
+        self.conv1 = nn.Conv1d(inplanes_P + inplanes_P, outplanes, 1)
+        self.bn1 = nn.BatchNorm1d(outplanes)
+
+    def forward(self, point_features, img_features):
+        img_features = self.IA_Layer(img_features, point_features)
+        return F.relu(self.bn1(self.conv1(torch.cat([point_features, img_features], dim=1))))
+
+
+class Pointnet2MSG(nn.Module):
+    """RPN backbone (pointnet2_msg.py:127-248)."""
+
+    def __init__(self, input_channels=None, use_xyz=None, config: BackboneConfig = None, ops=None, feature_gather=None):
+        super().__init__()
+        c = config or BackboneConfig()
+        if input_channels is not None:
+            c.input_channels = input_channels
+        if use_xyz is not None:
+            c.use_xyz = use_xyz
+        self.config = c
+        self._ops = ops or pointnet2_utils.OPS
+        # (feature_map (B,C,H,W), xy (B,N,2)) -> (B,C,N); the LI-Fusion boundary
+        self._feature_gather = feature_gather or (lambda fm, xy: li_fusion.feature_gather(fm, xy, c.align_corners))
+
+        self.SA_modules = nn.ModuleList()
+        channel_in = c.input_channels
+        skip_channel_list = [c.input_channels]
+        channel_out = channel_in
+        for k in range(len(c.npoints)):
+            mlps = [[channel_in] + list(spec) for spec in c.mlps[k]]
+            channel_out = sum(spec[-1] for spec in mlps)
+            self.SA_modules.append(PointnetSAModuleMSG(npoint=c.npoints[k], radii=c.radius[k], nsamples=c.nsample[k],
+                                                       mlps=mlps, use_xyz=c.use_xyz, bn=c.use_bn, ops=self._ops))
+            skip_channel_list.append(channel_out)
+            channel_in = channel_out
+
+        if c.li_fusion:
+            self.Img_Block = nn.ModuleList()
+            self.Fusion_Conv = nn.ModuleList()
+            self.DeConv = nn.ModuleList()
+            for i in range(len(c.img_channels) - 1):
+                self.Img_Block.append(BasicBlock(c.img_channels[i], c.img_channels[i + 1], stride=1))
+                if c.image_attention:
+                    self.Fusion_Conv.append(Atten_Fusion_Conv(c.img_channels[i + 1], c.point_channels[i], c.point_channels[i]))
+                else:
+                    self.Fusion_Conv.append(Fusion_Conv(c.img_channels[i + 1] + c.point_channels[i], c.point_channels[i]))
+                self.DeConv.append(nn.ConvTranspose2d(c.img_channels[i + 1], c.deconv_reduce[i],
+                                                      kernel_size=c.deconv_kernels[i], stride=c.deconv_kernels[i]))
+            quarter = c.img_features_channel // 4
+            self.image_fusion_conv = nn.Conv2d(sum(c.deconv_reduce), quarter, kernel_size=1)
+            self.image_fusion_bn = nn.BatchNorm2d(quarter)
+            if c.image_attention:
+                self.final_fusion_img_point = Atten_Fusion_Conv(quarter, c.img_features_channel, c.img_features_channel)
+            else:
+                self.final_fusion_img_point = Fusion_Conv(c.img_features_channel + quarter, c.img_features_channel)
+
+        self.FP_modules = nn.ModuleList()
+        for k in range(len(c.fp_mlps)):
+            pre_channel = c.fp_mlps[k + 1][-1] if k + 1 < len(c.fp_mlps) else channel_out
+            self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k]),
+                                                    ops=self._ops))
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, pointcloud: torch.Tensor, image=None, xy=None):
+        """pointcloud (B,N,3+C), image (B,3,H,W), xy (B,N,2) pixel coordinates -> (xyz (B,N,3), features (B,128,N)).
+        Like the reference (:208-210) `xy` is normalised IN PLACE: pass a fresh copy per call."""
+        c = self.config
+        xyz, features = self._break_up_pc(pointcloud)
+        l_xyz, l_features = [xyz], [features]
+
+        if c.li_fusion:
+            xy[:, :, 0] = xy[:, :, 0] / (c.image_size[0] - 1.0) * 2.0 - 1.0
+            xy[:, :, 1] = xy[:, :, 1] / (c.image_size[1] - 1.0) * 2.0 - 1.0
+            l_xy_cor = [xy]
+            img = [image]
+
+        for i in range(len(self.SA_modules)):
+            li_xyz, li_features, li_index = self.SA_modules[i](l_xyz[i], l_features[i])
+            if c.li_fusion:
+                gather_index = li_index.long().unsqueeze(-1).repeat(1, 1, 2)
+                li_xy_cor = torch.gather(l_xy_cor[i], 1, gather_index)
+                image = self.Img_Block[i](img[i])
+                img_gather_feature = self._feature_gather(image, li_xy_cor)
+                li_features = self.Fusion_Conv[i](li_features, img_gather_feature)
+                l_xy_cor.append(li_xy_cor)
+                img.append(image)
+            l_xyz.append(li_xyz)
+            l_features.append(li_features)
+
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+
+        if c.li_fusion:
+            de_concat = torch.cat([self.DeConv[i](img[i + 1]) for i in range(len(c.img_channels) - 1)], dim=1)
+            img_fusion = F.relu(self.image_fusion_bn(self.image_fusion_conv(de_concat)))
+            img_fusion_gather_feature = self._feature_gather(img_fusion, xy)
+            l_features[0] = self.final_fusion_img_point(l_features[0], img_fusion_gather_feature)
+
+        return l_xyz[0], l_features[0]

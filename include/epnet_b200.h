@@ -1,0 +1,76 @@
+/*
+ * epnet_b200.h -- C ABI of libepnet_b200.so, the B200 (sm_100a) implementation of EPNet's RPN-backbone
+ * point ops.  This is the drop-in boundary: every "reference-signature" entry point below takes exactly
+ * the arguments of the reference's kernel launcher it replaces (ints, a float radius, raw device
+ * pointers, a trailing CUDA stream) so that the reference's five .cpp wrappers -- or any FFI -- can bind
+ * it one for one.  Differences from the reference launchers, all deliberate:
+ *   - extern "C" (the reference's are C++-mangled);
+ *   - they return int: 0 on success, otherwise the cudaError_t of the failed launch or
+ *     EPNET_ERR_BAD_ARG; they never call exit() (the reference prints and exit(-1)s,
+ *     e.g. sampling_gpu.cu:248-252);
+ *   - `stream` is passed as void* (a cudaStream_t) so the header needs no CUDA include.
+ * Contract kept from the reference: the caller owns every buffer (outputs, the FPS `temp` scratch,
+ * zero-filled gradient buffers, zero-filled ball-query idx); nothing here allocates, frees or
+ * synchronises; all tensors are contiguous fp32 / int32; the library is re-entrant.
+ *
+ * Reference paths are relative to /root/reference/pointnet2_lib/pointnet2/src/.
+ */
+#ifndef EPNET_B200_H
+#define EPNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPNET_OK 0
+#define EPNET_ERR_BAD_ARG (-1)
+
+/* ABI version of this header; bumped when a signature changes. */
+int epnet_abi_version(void);
+/* Human-readable text for a code returned by any entry point. */
+const char *epnet_error_string(int code);
+
+/* ---- reference-signature entry points ------------------------------------------------------ */
+
+/* replaces furthest_point_sampling_kernel_launcher (sampling_gpu.h:26, sampling_gpu.cu:211-253).
+ * xyz (B,N,3); temp (B,N) in/out running min squared distance, pre-filled by the caller with 1e10
+ * (pointnet2_utils.py:26), must be >= 0 and not NaN; idx (B,M) out.  Bit-exact with the reference,
+ * including which of several equally distant points wins. */
+int epnet_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream);
+
+/* replaces gather_points_kernel_launcher_fast (sampling_gpu.h:12): out[b,c,j] = points[b,c,idx[b,j]] */
+int epnet_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out, void *stream);
+/* replaces gather_points_grad_kernel_launcher_fast (sampling_gpu.h:19); grad_points arrives zeroed */
+int epnet_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx, float *grad_points, void *stream);
+
+/* replaces ball_query_kernel_launcher_fast (ball_query_gpu.h:12; argument ORDER as in
+ * ball_query_gpu.cu:48-49: query centres first, then the cloud).  new_xyz (B,M,3), xyz (B,N,3),
+ * idx (B,M,nsample) arrives zeroed. */
+int epnet_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx, void *stream);
+
+/* replaces group_points_kernel_launcher_fast (group_points_gpu.h:13): out[b,c,p,s] = points[b,c,idx[b,p,s]] */
+int epnet_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out, void *stream);
+/* replaces group_points_grad_kernel_launcher_fast (group_points_gpu.h:19); grad_points arrives zeroed */
+int epnet_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx, float *grad_points, void *stream);
+
+/* replaces three_nn_kernel_launcher_fast (interpolate_gpu.h:13). unknown (B,n,3), known (B,m,3) ->
+ * dist2 (B,n,3) SQUARED distances (the Python layer takes the sqrt, pointnet2_utils.py:98), idx (B,n,3) */
+int epnet_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *stream);
+/* replaces three_interpolate_kernel_launcher_fast (interpolate_gpu.h:20). points (B,C,m), idx/weight (B,n,3) -> out (B,C,n) */
+int epnet_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out, void *stream);
+/* replaces three_interpolate_grad_kernel_launcher_fast (interpolate_gpu.h:27); grad_points (B,C,m) arrives zeroed */
+int epnet_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, void *stream);
+
+/* ---- LI-Fusion gather ---------------------------------------------------------------------- */
+
+/* replaces the torch.nn.functional.grid_sample call of Feature_Gather
+ * (/root/reference/lib/net/pointnet2_msg.py:107-120): bilinear, zero padding, one row of N sample
+ * points per scene.  fmap (B,C,H,W) NCHW, xy (B,N,2) in [-1,1] (x->W, y->H) -> out (B,C,N). */
+int epnet_grid_gather_bilinear(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, void *stream);
+/* gradient w.r.t. fmap; grad_fmap (B,C,H,W) arrives zeroed */
+int epnet_grid_gather_bilinear_grad(int b, int c, int h, int w, int n, const float *grad_out, const float *xy, int align_corners, float *grad_fmap, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPNET_B200_H */

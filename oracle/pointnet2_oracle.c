@@ -1,0 +1,295 @@
+/*
+ * oracle/pointnet2_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU restatement of the arithmetic of EPNet's pointnet2 CUDA ops and of the
+ * LI-Fusion bilinear image gather.  It exists so that the CUDA kernels in
+ * epnet_b200/csrc can be checked bit-for-bit (indices) and to 1e-5 (floats).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it.
+ *
+ * Parity status: the reference ships no tests or golden vectors, so this
+ * file is pinned against the reference's own, unmodified kernels compiled into
+ * oracle/_ref/libpointnet2_ref.so and executed on a B200 (tests/test_ref_pin.py, `-m gpu`),
+ * and against fixtures under tests/golden/ produced by that library.
+ *
+ * All distance computations reproduce the FMA contraction nvcc -O2 emits for the reference
+ * source (checked in PTX): d = fmaf(dz,dz, fmaf(dx,dx, dy*dy)).  Build with -ffp-contract=off.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * /root/reference/pointnet2_lib/pointnet2/src/).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+static inline float sqdist_contracted(float ax, float ay, float az, float bx, float by, float bz)
+{
+    /* (a-b) per axis, then y*y first, x fused on top, z fused last: the order nvcc picks. */
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+/* cuda_utils.h:10-14 -- thread count of the FPS block: largest power of two <= n, capped at 1024.
+ * The reference computes it through a double log; this integer form is equal for every n we use
+ * (asserted against the log formula in tests/test_oracle.py). */
+ORACLE_API int oracle_fps_block_size(int n)
+{
+    int p = 1;
+    while (p * 2 <= n && p * 2 <= 1024) p *= 2;
+    return p;
+}
+
+/* sampling_gpu.cu:93-209 -- furthest point sampling, including the shared-memory tree reduction
+ * whose tie handling (keep the lower slot unless the upper one is strictly larger) decides which
+ * of several equally distant points is sampled.  temp is read AND written, as in the reference:
+ * the caller pre-fills it with 1e10 (pointnet2_utils.py:26). */
+ORACLE_API void oracle_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx)
+{
+    if (m <= 0) return;
+    const int bs = oracle_fps_block_size(n);
+    float *slot_val = (float *)malloc(sizeof(float) * (size_t)bs);
+    int *slot_idx = (int *)malloc(sizeof(int) * (size_t)bs);
+
+    for (int s = 0; s < b; ++s) {
+        const float *p = xyz + (size_t)s * n * 3;
+        float *t = temp + (size_t)s * n;
+        int *out = idx + (size_t)s * m;
+        int last = 0;
+        out[0] = 0;
+        for (int j = 1; j < m; ++j) {
+            const float lx = p[last * 3 + 0], ly = p[last * 3 + 1], lz = p[last * 3 + 2];
+            /* per-"thread" strided scan: strict '>' keeps the first maximum (:129-138) */
+            for (int tid = 0; tid < bs; ++tid) {
+                float best = -1.0f;
+                int besti = 0;
+                for (int k = tid; k < n; k += bs) {
+                    const float d = sqdist_contracted(p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2], lx, ly, lz);
+                    const float d2 = fminf(d, t[k]);
+                    t[k] = d2;
+                    if (d2 > best) { best = d2; besti = k; }
+                }
+                slot_val[tid] = best;
+                slot_idx[tid] = besti;
+            }
+            /* tree reduction (:143-203) with __update (:86-91) */
+            for (int half = bs / 2; half >= 1; half /= 2) {
+                for (int tid = 0; tid < half; ++tid) {
+                    const float v1 = slot_val[tid], v2 = slot_val[tid + half];
+                    if (v2 > v1) { slot_val[tid] = v2; slot_idx[tid] = slot_idx[tid + half]; }
+                }
+            }
+            last = slot_idx[0];
+            out[j] = last;
+        }
+    }
+    free(slot_val);
+    free(slot_idx);
+}
+
+/* sampling_gpu.cu:8-24 */
+ORACLE_API void oracle_gather_points(int b, int c, int n, int m, const float *points, const int *idx, float *out)
+{
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *src = points + ((size_t)s * c + ch) * n;
+            float *dst = out + ((size_t)s * c + ch) * m;
+            const int *id = idx + (size_t)s * m;
+            for (int j = 0; j < m; ++j) dst[j] = src[id[j]];
+        }
+}
+
+/* sampling_gpu.cu:46-63 -- scatter-add; the reference's atomic order is unspecified, so callers
+ * compare with a tolerance.  grad_points must arrive zeroed (pointnet2_utils.py:67). */
+ORACLE_API void oracle_gather_points_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, float *grad_points)
+{
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *g = grad_out + ((size_t)s * c + ch) * m;
+            float *dst = grad_points + ((size_t)s * c + ch) * n;
+            const int *id = idx + (size_t)s * m;
+            for (int j = 0; j < m; ++j) dst[id[j]] += g[j];
+        }
+}
+
+/* ball_query_gpu.cu:9-45 -- ascending scan, strict d2 < r*r (r*r rounded in float, :23); the first
+ * hit fills every slot, later hits overwrite slots 1..; idx arrives zeroed (pointnet2_utils.py:218)
+ * so a centre without any hit keeps zeros. */
+ORACLE_API void oracle_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx)
+{
+    const float r2 = radius * radius;
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int s = 0; s < b; ++s)
+        for (int j = 0; j < m; ++j) {
+            const float *q = new_xyz + ((size_t)s * m + j) * 3;
+            const float *p = xyz + (size_t)s * n * 3;
+            int *o = idx + ((size_t)s * m + j) * nsample;
+            int cnt = 0;
+            for (int k = 0; k < n && cnt < nsample; ++k) {
+                const float d2 = sqdist_contracted(q[0], q[1], q[2], p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2]);
+                if (d2 < r2) {
+                    if (cnt == 0)
+                        for (int l = 0; l < nsample; ++l) o[l] = k;
+                    o[cnt++] = k;
+                }
+            }
+        }
+}
+
+/* group_points_gpu.cu:47-66 */
+ORACLE_API void oracle_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out)
+{
+    const size_t per = (size_t)npoints * nsample;
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *src = points + ((size_t)s * c + ch) * n;
+            float *dst = out + ((size_t)s * c + ch) * per;
+            const int *id = idx + (size_t)s * per;
+            for (size_t e = 0; e < per; ++e) dst[e] = src[id[e]];
+        }
+}
+
+/* group_points_gpu.cu:8-25 */
+ORACLE_API void oracle_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx, float *grad_points)
+{
+    const size_t per = (size_t)npoints * nsample;
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *g = grad_out + ((size_t)s * c + ch) * per;
+            float *dst = grad_points + ((size_t)s * c + ch) * n;
+            const int *id = idx + (size_t)s * per;
+            for (size_t e = 0; e < per; ++e) dst[id[e]] += g[e];
+        }
+}
+
+/* interpolate_gpu.cu:9-52 -- three smallest squared distances by a strict-'<' cascade: equal
+ * distances keep the lower index first.  The reference holds the running bests in double (init
+ * 1e40) but compares exactly-widened floats, so float compares with an "unset" marker are
+ * equivalent; unset slots come out as +inf / index 0, the float conversion of 1e40. */
+ORACLE_API void oracle_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx)
+{
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int s = 0; s < b; ++s)
+        for (int j = 0; j < n; ++j) {
+            const float *u = unknown + ((size_t)s * n + j) * 3;
+            const float *kn = known + (size_t)s * m * 3;
+            double b1 = 1e40, b2 = 1e40, b3 = 1e40;
+            int i1 = 0, i2 = 0, i3 = 0;
+            for (int k = 0; k < m; ++k) {
+                const double d = (double)sqdist_contracted(u[0], u[1], u[2], kn[k * 3 + 0], kn[k * 3 + 1], kn[k * 3 + 2]);
+                if (d < b1)      { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+                else if (d < b3) { b3 = d; i3 = k; }
+            }
+            float *od = dist2 + ((size_t)s * n + j) * 3;
+            int *oi = idx + ((size_t)s * n + j) * 3;
+            od[0] = (float)b1; od[1] = (float)b2; od[2] = (float)b3;
+            oi[0] = i1; oi[1] = i2; oi[2] = i3;
+        }
+}
+
+/* interpolate_gpu.cu:77-97 -- contraction order from PTX: fma(w2,p2, fma(w0,p0, w1*p1)). */
+ORACLE_API void oracle_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out)
+{
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *src = points + ((size_t)s * c + ch) * m;
+            float *dst = out + ((size_t)s * c + ch) * n;
+            for (int j = 0; j < n; ++j) {
+                const int *id = idx + ((size_t)s * n + j) * 3;
+                const float *w = weight + ((size_t)s * n + j) * 3;
+                dst[j] = fmaf(w[2], src[id[2]], fmaf(w[0], src[id[0]], w[1] * src[id[1]]));
+            }
+        }
+}
+
+/* interpolate_gpu.cu:120-142 */
+ORACLE_API void oracle_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points)
+{
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *g = grad_out + ((size_t)s * c + ch) * n;
+            float *dst = grad_points + ((size_t)s * c + ch) * m;
+            for (int j = 0; j < n; ++j) {
+                const int *id = idx + ((size_t)s * n + j) * 3;
+                const float *w = weight + ((size_t)s * n + j) * 3;
+                dst[id[0]] += g[j] * w[0];
+                dst[id[1]] += g[j] * w[1];
+                dst[id[2]] += g[j] * w[2];
+            }
+        }
+}
+
+/* LI-Fusion gather: lib/net/pointnet2_msg.py:107-120 calls torch.nn.functional.grid_sample
+ * (ATen grid_sampler_2d; third-party, torch 2.11.0 in this image, not under /root/reference) with
+ * mode='bilinear', padding_mode='zeros'.  Restated from its published algorithm: unnormalise
+ *   align_corners: ix = (x+1)/2*(W-1)      else: ix = ((x+1)*W-1)/2
+ * floor to the NW corner, weights nw=(ixe-ix)(iye-iy) ..., out-of-range taps contribute zero,
+ * taps summed in the order nw, ne, sw, se.  Anchored on torch's own CPU grid_sample in
+ * tests/test_oracle.py (<=1e-6 abs); float, not bit-exact. */
+ORACLE_API void oracle_grid_gather_bilinear(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out)
+{
+    #pragma omp parallel for collapse(2) schedule(static)
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            const float *img = fmap + ((size_t)s * c + ch) * h * w;
+            float *dst = out + ((size_t)s * c + ch) * n;
+            for (int j = 0; j < n; ++j) {
+                const float gx = xy[((size_t)s * n + j) * 2 + 0], gy = xy[((size_t)s * n + j) * 2 + 1];
+                float ix, iy;
+                if (align_corners) {
+                    ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
+                    iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+                } else {
+                    ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
+                    iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+                }
+                const float fx = floorf(ix), fy = floorf(iy);
+                const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+                const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+                const float wne = (ix - (float)x0) * ((float)y1 - iy);
+                const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+                const float wse = (ix - (float)x0) * (iy - (float)y0);
+                float acc = 0.f;
+                if (x0 >= 0 && x0 < w && y0 >= 0 && y0 < h) acc += img[(size_t)y0 * w + x0] * wnw;
+                if (x1 >= 0 && x1 < w && y0 >= 0 && y0 < h) acc += img[(size_t)y0 * w + x1] * wne;
+                if (x0 >= 0 && x0 < w && y1 >= 0 && y1 < h) acc += img[(size_t)y1 * w + x0] * wsw;
+                if (x1 >= 0 && x1 < w && y1 >= 0 && y1 < h) acc += img[(size_t)y1 * w + x1] * wse;
+                dst[j] = acc;
+            }
+        }
+}
+
+/* Backward of the gather w.r.t. the feature map (xy carries no gradient on the hot path). */
+ORACLE_API void oracle_grid_gather_bilinear_grad(int b, int c, int h, int w, int n, const float *grad_out, const float *xy, int align_corners, float *grad_fmap)
+{
+    for (int s = 0; s < b; ++s)
+        for (int ch = 0; ch < c; ++ch) {
+            float *img = grad_fmap + ((size_t)s * c + ch) * h * w;
+            const float *g = grad_out + ((size_t)s * c + ch) * n;
+            for (int j = 0; j < n; ++j) {
+                const float gx = xy[((size_t)s * n + j) * 2 + 0], gy = xy[((size_t)s * n + j) * 2 + 1];
+                float ix, iy;
+                if (align_corners) {
+                    ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
+                    iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+                } else {
+                    ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
+                    iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+                }
+                const float fx = floorf(ix), fy = floorf(iy);
+                const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+                const float wnw = ((float)x1 - ix) * ((float)y1 - iy);
+                const float wne = (ix - (float)x0) * ((float)y1 - iy);
+                const float wsw = ((float)x1 - ix) * (iy - (float)y0);
+                const float wse = (ix - (float)x0) * (iy - (float)y0);
+                if (x0 >= 0 && x0 < w && y0 >= 0 && y0 < h) img[(size_t)y0 * w + x0] += g[j] * wnw;
+                if (x1 >= 0 && x1 < w && y0 >= 0 && y0 < h) img[(size_t)y0 * w + x1] += g[j] * wne;
+                if (x0 >= 0 && x0 < w && y1 >= 0 && y1 < h) img[(size_t)y1 * w + x0] += g[j] * wsw;
+                if (x1 >= 0 && x1 < w && y1 >= 0 && y1 < h) img[(size_t)y1 * w + x1] += g[j] * wse;
+            }
+        }
+}

@@ -1,0 +1,103 @@
+"""oracle/ref_cuda.py -- TEST INFRASTRUCTURE.  The reference's OWN, unmodified CUDA kernels
+(oracle/_ref/libpointnet2_ref.so, built by oracle/build_ref.sh) behind the nine `*_wrapper` names of the
+reference's pybind table, so tests can pin the oracle and the product kernels against the real thing on
+a B200, and bench.py --impl reference can time it.  Never imported by epnet_b200/.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import REF_LIB_PATH
+
+_c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+
+def available():
+    return os.path.exists(REF_LIB_PATH)
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libpointnet2_ref.so not built; run oracle/build_ref.sh where /root/reference exists")
+        lib = ctypes.CDLL(REF_LIB_PATH)
+        sigs = {
+            "ref_furthest_point_sampling": [_c_int] * 3 + [_c_void_p] * 4,
+            "ref_gather_points": [_c_int] * 4 + [_c_void_p] * 4,
+            "ref_gather_points_grad": [_c_int] * 4 + [_c_void_p] * 4,
+            "ref_ball_query": [_c_int] * 3 + [_c_float, _c_int] + [_c_void_p] * 4,
+            "ref_group_points": [_c_int] * 5 + [_c_void_p] * 4,
+            "ref_group_points_grad": [_c_int] * 5 + [_c_void_p] * 4,
+            "ref_three_nn": [_c_int] * 3 + [_c_void_p] * 5,
+            "ref_three_interpolate": [_c_int] * 4 + [_c_void_p] * 5,
+            "ref_three_interpolate_grad": [_c_int] * 4 + [_c_void_p] * 5,
+        }
+        for name, argtypes in sigs.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = None
+        _lib = lib
+    return _lib
+
+
+def _p(t):
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def _s(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
+    _load().ref_furthest_point_sampling(b, n, m, _p(points_tensor), _p(temp_tensor), _p(idx_tensor), _s(points_tensor))
+    return 1
+
+
+def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tensor):
+    _load().ref_gather_points(b, c, n, npoints, _p(points_tensor), _p(idx_tensor), _p(out_tensor), _s(points_tensor))
+    return 1
+
+
+def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, grad_points_tensor):
+    _load().ref_gather_points_grad(b, c, n, npoints, _p(grad_out_tensor), _p(idx_tensor), _p(grad_points_tensor),
+                                   _s(grad_out_tensor))
+    return 1
+
+
+def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
+    _load().ref_ball_query(b, n, m, float(radius), nsample, _p(new_xyz_tensor), _p(xyz_tensor), _p(idx_tensor),
+                           _s(xyz_tensor))
+    return 1
+
+
+def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, out_tensor):
+    _load().ref_group_points(b, c, n, npoints, nsample, _p(points_tensor), _p(idx_tensor), _p(out_tensor),
+                             _s(points_tensor))
+    return 1
+
+
+def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor, grad_points_tensor):
+    _load().ref_group_points_grad(b, c, n, npoints, nsample, _p(grad_out_tensor), _p(idx_tensor),
+                                  _p(grad_points_tensor), _s(grad_out_tensor))
+    return 1
+
+
+def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
+    _load().ref_three_nn(b, n, m, _p(unknown_tensor), _p(known_tensor), _p(dist2_tensor), _p(idx_tensor),
+                         _s(unknown_tensor))
+
+
+def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
+    _load().ref_three_interpolate(b, c, m, n, _p(points_tensor), _p(idx_tensor), _p(weight_tensor), _p(out_tensor),
+                                  _s(points_tensor))
+
+
+def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
+    _load().ref_three_interpolate_grad(b, c, n, m, _p(grad_out_tensor), _p(idx_tensor), _p(weight_tensor),
+                                       _p(grad_points_tensor), _s(grad_out_tensor))

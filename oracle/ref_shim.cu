@@ -1,0 +1,39 @@
+// oracle/ref_shim.cu -- TEST INFRASTRUCTURE.  extern "C" doors onto the reference's own, unmodified
+// kernel launchers (declared in /root/reference/pointnet2_lib/pointnet2/src/*_gpu.h), so they can
+// be driven through ctypes without torch's C++ API (the reference's .cpp wrappers need THC, which
+// torch >= 1.11 no longer ships).  Built only by oracle/build_ref.sh into oracle/_ref/.
+#include <cuda_runtime_api.h>
+#include "ball_query_gpu.h"
+#include "group_points_gpu.h"
+#include "interpolate_gpu.h"
+#include "sampling_gpu.h"
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+REF_API void ref_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream)
+{ furthest_point_sampling_kernel_launcher(b, n, m, xyz, temp, idx, (cudaStream_t)stream); }
+
+REF_API void ref_gather_points(int b, int c, int n, int m, const float *points, const int *idx, float *out, void *stream)
+{ gather_points_kernel_launcher_fast(b, c, n, m, points, idx, out, (cudaStream_t)stream); }
+
+REF_API void ref_gather_points_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, float *grad_points, void *stream)
+{ gather_points_grad_kernel_launcher_fast(b, c, n, m, grad_out, idx, grad_points, (cudaStream_t)stream); }
+
+// first pointer = query centres (new_xyz), second = cloud (xyz): ball_query_gpu.cu:48-49 / ball_query.cpp:23
+REF_API void ref_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx, void *stream)
+{ ball_query_kernel_launcher_fast(b, n, m, radius, nsample, new_xyz, xyz, idx, (cudaStream_t)stream); }
+
+REF_API void ref_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out, void *stream)
+{ group_points_kernel_launcher_fast(b, c, n, npoints, nsample, points, idx, out, (cudaStream_t)stream); }
+
+REF_API void ref_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx, float *grad_points, void *stream)
+{ group_points_grad_kernel_launcher_fast(b, c, n, npoints, nsample, grad_out, idx, grad_points, (cudaStream_t)stream); }
+
+REF_API void ref_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *stream)
+{ three_nn_kernel_launcher_fast(b, n, m, unknown, known, dist2, idx, (cudaStream_t)stream); }
+
+REF_API void ref_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out, void *stream)
+{ three_interpolate_kernel_launcher_fast(b, c, m, n, points, idx, weight, out, (cudaStream_t)stream); }
+
+REF_API void ref_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, void *stream)
+{ three_interpolate_grad_kernel_launcher_fast(b, c, n, m, grad_out, idx, weight, grad_points, (cudaStream_t)stream); }

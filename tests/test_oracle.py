@@ -1,0 +1,134 @@
+"""CPU tests of the oracle itself (no GPU): the C restatement against independent numpy statements of
+the same rules, against torch's CPU grid_sample, and on the edge cases the GPU parity tests rely on."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cases import cloud
+
+
+def test_fps_block_size_matches_reference_log_formula():
+    # cuda_utils.h:10-14 computes 2^int(log(n)/log(2)) capped to [1,1024] in double arithmetic
+    for n in list(range(1, 5000)) + [8191, 8192, 16383, 16384, 65536, 131072, 199999]:
+        pow2 = int(math.log(float(n)) / math.log(2.0))
+        assert oracle.fps_block_size(n) == max(min(1 << pow2, 1024), 1), n
+
+
+@pytest.mark.parametrize("kind,n,m", [("gauss", 257, 64), ("lattice", 300, 120), ("lattice", 2100, 200),
+                                      ("identical", 70, 20), ("gauss", 1, 1), ("gauss", 3, 3), ("uniform", 1500, 300)])
+def test_fps_thread_tree_emulation_equals_tie_rule(kind, n, m):
+    xyz = cloud(3, 2, n, kind, dup_frac=0.1 if n > 50 else 0.0)
+    got = oracle.furthest_point_sampling(xyz, m)
+    want = oracle.fps_tie_rule_bruteforce(xyz, m)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_fps_tie_is_not_lowest_index():
+    # a tie between k=3 and k=513 at BS=1024 goes to 513 (bit-reversed slot order)
+    n = 2048
+    xyz = np.zeros((1, n, 3), dtype=np.float32)
+    xyz[0, 3] = xyz[0, 513] = [5, 0, 0]
+    idx = oracle.furthest_point_sampling(xyz, 2)
+    assert idx[0, 1] == 513
+
+
+def test_fps_temp_is_running_min_distance():
+    xyz = cloud(5, 1, 500, "gauss")
+    idx, temp = oracle.furthest_point_sampling(xyz, 50, return_temp=True)
+    d = ((xyz[0][:, None, :] - xyz[0][idx[0]][None, :, :]) ** 2).sum(-1)[:, :-1].min(1)  # last sample never applied
+    np.testing.assert_allclose(temp[0], d, rtol=1e-5, atol=1e-6)
+    assert len(set(idx[0].tolist())) == 50
+
+
+def _ball_query_numpy(radius, nsample, xyz, new_xyz):
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    out = np.zeros((B, M, nsample), dtype=np.int32)
+    r2 = np.float32(radius) * np.float32(radius)
+    for b in range(B):
+        for j in range(M):
+            d = new_xyz[b, j] - xyz[b]
+            t = (d[:, 1].astype(np.float64) ** 2).astype(np.float32)
+            t = (d[:, 0].astype(np.float64) ** 2 + t).astype(np.float32)
+            t = (d[:, 2].astype(np.float64) ** 2 + t).astype(np.float32)
+            hits = np.nonzero(t < r2)[0][:nsample]
+            if len(hits):
+                out[b, j, :] = hits[0]
+                out[b, j, :len(hits)] = hits
+    return out
+
+
+@pytest.mark.parametrize("radius,nsample", [(0.3, 16), (1.0, 32), (1e-4, 8), (100.0, 5)])
+def test_ball_query_order_padding_and_empty(radius, nsample):
+    xyz = cloud(7, 2, 700, "gauss", dup_frac=0.05)
+    new_xyz = np.ascontiguousarray(xyz[:, ::7] + (0 if radius > 1e-3 else 1.0))
+    got = oracle.ball_query(radius, nsample, xyz, new_xyz)
+    np.testing.assert_array_equal(got, _ball_query_numpy(radius, nsample, xyz, new_xyz))
+    if radius < 1e-3:
+        assert (got == 0).all()  # no neighbour anywhere: the caller's zero fill survives
+
+
+def test_three_nn_lexicographic_ties_and_short_known():
+    unknown = cloud(9, 2, 300, "lattice")
+    known = cloud(10, 2, 90, "lattice")
+    d2, idx = oracle.three_nn(unknown, known)
+    full = ((unknown[:, :, None, :] - known[:, None, :, :]) ** 2).sum(-1)
+    order = np.argsort(full, axis=2, kind="stable")[:, :, :3]  # stable = lower index first among ties
+    np.testing.assert_array_equal(idx, order.astype(np.int32))
+    np.testing.assert_array_equal(d2, np.take_along_axis(full, order, 2))
+    d2s, idxs = oracle.three_nn(unknown, known[:, :2])  # m < 3: unfilled slot = +inf / index 0
+    assert np.isinf(d2s[..., 2]).all() and (idxs[..., 2] == 0).all()
+
+
+def test_gather_group_interpolate_definitions():
+    rng = np.random.RandomState(0)
+    pts = rng.randn(2, 5, 40).astype(np.float32)
+    idx = rng.randint(0, 40, size=(2, 9, 4)).astype(np.int32)
+    g = oracle.group_points(pts, idx)
+    for b in range(2):
+        np.testing.assert_array_equal(g[b], pts[b][:, idx[b]])
+    np.testing.assert_array_equal(oracle.gather_points(pts, idx[:, :, 0]), g[..., 0])
+    w = rng.rand(2, 9, 3).astype(np.float32)
+    out = oracle.three_interpolate(pts, idx[:, :, :3], w)
+    want = (g[..., :3].astype(np.float64) * w[:, None].astype(np.float64)).sum(-1)
+    np.testing.assert_allclose(out, want, rtol=1e-6, atol=1e-6)
+
+
+def test_grads_are_transposes_of_forward():
+    rng = np.random.RandomState(1)
+    pts = rng.randn(2, 3, 30).astype(np.float32)
+    idx = rng.randint(0, 30, size=(2, 8, 5)).astype(np.int32)
+    go = rng.randn(2, 3, 8, 5).astype(np.float32)
+    lhs = (oracle.group_points(pts, idx).astype(np.float64) * go).sum()
+    rhs = (oracle.group_points_grad(go, idx, 30).astype(np.float64) * pts).sum()
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    w = rng.rand(2, 8, 3).astype(np.float32)
+    go3 = rng.randn(2, 3, 8).astype(np.float32)
+    lhs = (oracle.three_interpolate(pts, idx[:, :, :3], w).astype(np.float64) * go3).sum()
+    rhs = (oracle.three_interpolate_grad(go3, idx[:, :, :3], w, 30).astype(np.float64) * pts).sum()
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    lhs = (oracle.gather_points(pts, idx[:, :, 0]).astype(np.float64) * go[..., 0]).sum()
+    rhs = (oracle.gather_points_grad(go[..., 0], idx[:, :, 0], 30).astype(np.float64) * pts).sum()
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+
+
+@pytest.mark.parametrize("align_corners", [False, True])
+def test_grid_gather_matches_torch_cpu_grid_sample(align_corners):
+    rng = np.random.RandomState(2)
+    fmap = rng.randn(2, 6, 12, 20).astype(np.float32)
+    xy = (rng.rand(2, 200, 2).astype(np.float32) * 2.4 - 1.2)  # includes points outside [-1,1]
+    xy[0, 0] = [-1, -1]; xy[0, 1] = [1, 1]; xy[0, 2] = [0, 0]; xy[0, 3] = [1.0, -1.0]
+    got = oracle.grid_gather_bilinear(fmap, xy, align_corners)
+    want = torch.nn.functional.grid_sample(torch.from_numpy(fmap), torch.from_numpy(xy).unsqueeze(1), mode="bilinear",
+                                           padding_mode="zeros", align_corners=align_corners).squeeze(2).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    # backward against autograd
+    f = torch.from_numpy(fmap).requires_grad_(True)
+    out = torch.nn.functional.grid_sample(f, torch.from_numpy(xy).unsqueeze(1), align_corners=align_corners).squeeze(2)
+    go = torch.from_numpy(rng.randn(*out.shape).astype(np.float32))
+    out.backward(go)
+    got_g = oracle.grid_gather_bilinear_grad(go.numpy(), xy, 12, 20, align_corners)
+    np.testing.assert_allclose(got_g, f.grad.numpy(), rtol=1e-4, atol=1e-5)
