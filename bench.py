@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Headline benchmark: EPNet RPN-backbone forward (4-level SA-MSG + FP + LI-Fusion with image attention),
+16384 points + 384x1280 image per scene, batch 2 per GPU, fp32 -- BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one backbone forward over one batch of synthetic KITTI-shaped scenes (epnet_b200/scenes.py) with
+random-init weights (torch.manual_seed(0)).  Prints ONE JSON line on rank 0.
+  value : scenes/s, inputs already resident in HBM (a 24-batch pool > L2 is rotated through, so no step
+          finds its inputs in L2), device-timed with CUDA events, max over ranks.
+  e2e   : scenes/s through the public module call with HOST (pinned) inputs: H2D of points/image/xy and
+          D2H of the (B,128,N) features + xyz inside the timed region.
+--impl reference runs the same network, weights, inputs and precision on the reference's OWN CUDA kernels
+(oracle/_ref/libpointnet2_ref.so built from the unmodified sources) in the reference's op-by-op composition,
+with ATen's grid_sample -- the "reference CUDA extension on the same B200" baseline of BASELINE.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 2
+NPOINTS = 16384
+POOL = 24  # resident input batches rotated through: 24 x 12.4 MB = 298 MB > 126 MB L2
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- models
+def build_model(impl, device):
+    from epnet_b200 import BackboneConfig, Pointnet2MSG
+    torch.manual_seed(0)
+    if impl == "ours":
+        model = Pointnet2MSG(config=BackboneConfig())
+    else:
+        from epnet_b200.pointnet2_utils import make_ops
+        from oracle import ref_cuda
+        ops = make_ops(ref_cuda)
+
+        def aten_gather(fm, xy):  # the reference's Feature_Gather, verbatim semantics (pointnet2_msg.py:107-120)
+            return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
+
+        model = Pointnet2MSG(config=BackboneConfig(), ops=ops, feature_gather=aten_gather, reference_composition=True)
+    return model.to(device).eval()
+
+
+def make_pool(n_batches, first_seed):
+    from epnet_b200 import scenes
+    return [scenes.batch(first_seed + 10 * i, BATCH_PER_GPU, NPOINTS) for i in range(n_batches)]
+
+
+# ----------------------------------------------------------------------------------------- timing
+def timed_region(fn, steps, rank_sync):
+    rank_sync()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        fn(i)
+    end.record()
+    torch.cuda.synchronize()
+    rank_sync()
+    return start.elapsed_time(end)  # ms
+
+
+def cpu_baseline_leg(sample_scenes=1):
+    """Pure-PyTorch CPU implementation of the same backbone (oracle/torch_cpu.py ops + torch CPU convs) on
+    `sample_scenes` scene(s) of the workload, all host cores."""
+    from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
+    from epnet_b200.pointnet2_utils import make_ops
+    from oracle import torch_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+
+    def cpu_gather(fm, xy):
+        return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
+
+    model = Pointnet2MSG(config=BackboneConfig(), ops=make_ops(torch_cpu), feature_gather=cpu_gather,
+                         reference_composition=True).eval()
+    data = scenes.batch(1000, sample_scenes, NPOINTS)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        model(data["points"], data["image"], data["xy"].clone())
+        dt = time.perf_counter() - t0
+    return {"value": round(sample_scenes / dt, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": "%d scene(s) of the batch, one full backbone forward, pure-PyTorch CPU ops (oracle/torch_cpu.py)" % sample_scenes,
+            "seconds": round(dt, 2)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--tf32", type=int, default=0, help="allow TF32 in cuDNN/cuBLAS (default 0: strict fp32 in both arms)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="ours: run eagerly instead of replaying the captured CUDA graph")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = True
+
+    def rank_sync():
+        if distributed:
+            dist.barrier()
+
+    from epnet_b200 import pointnet2_cuda
+    model = build_model(args.impl, device)
+    host_pool = make_pool(POOL, 1000 + 1000 * rank)
+    dev_pool = [{k: v.to(device) for k, v in b.items()} for b in host_pool]
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_pool[:4]]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+
+    use_graph = args.impl == "ours" and not args.no_graph and hasattr(model, "make_runner")
+    runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device) if use_graph else None
+
+    out_host = None
+
+    def step_resident(i):
+        b = dev_pool[i % POOL]
+        with torch.no_grad():
+            if runner is not None:
+                return runner(b["points"], b["image"], b["xy"])
+            return model(b["points"], b["image"], b["xy"].clone())  # the model normalises xy in place
+
+    def step_e2e(i):
+        nonlocal out_host
+        hb = pinned[i % len(pinned)]
+        pts = hb["points"].to(device, non_blocking=True)
+        img = hb["image"].to(device, non_blocking=True)
+        xy = hb["xy"].to(device, non_blocking=True)
+        with torch.no_grad():
+            xyz, feats = runner(pts, img, xy) if runner is not None else model(pts, img, xy)
+        if out_host is None:
+            out_host = (torch.empty(xyz.shape, dtype=xyz.dtype).pin_memory(), torch.empty(feats.shape, dtype=feats.dtype).pin_memory())
+        out_host[0].copy_(xyz, non_blocking=True)
+        out_host[1].copy_(feats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller owns the result on the host before the next step
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pointnet2_cuda.LAUNCHES[0] = 0
+    ms = timed_region(step_resident, args.steps, rank_sync)
+    launches = pointnet2_cuda.LAUNCHES[0] if runner is None else runner.kernel_launches_per_replay * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed_region(step_e2e, args.steps, rank_sync)
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host)
+
+    if distributed:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+    scenes_total = BATCH_PER_GPU * world * args.steps
+    line = {
+        "metric": "RPN backbone scenes/s (forward, 16384 pts + 384x1280 image, LI-Fusion with attention)",
+        "value": round(scenes_total / (ms / 1e3), 3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: EPNet RPN backbone forward, batch 2 per GPU, 16384 pts, "
+                               "384x1280 image, LI-Fusion + image attention, eval-mode BN, random-init weights",
+                   "batch_per_gpu": BATCH_PER_GPU, "npoints": NPOINTS, "tf32": bool(args.tf32),
+                   "l2": "inputs rotate over a %d-batch resident pool (%.0f MB > 126 MB L2)" % (POOL, POOL * h2d_bytes / 1e6),
+                   "parallelism": "dp%d (independent scenes per GPU, no collective in the forward)" % world,
+                   "cuda_graph": bool(runner is not None)},
+        "e2e": {"value": round(scenes_total / (ms_e2e / 1e3), 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": "scenes/s", "cores": 0, "kind": "reference",
+                                "sample": "not a CPU run: the reference's own pointnet2 CUDA kernels (unmodified sources compiled "
+                                          "for sm_100a into oracle/_ref) under the reference's op-by-op module composition and ATen "
+                                          "grid_sample, same B200, same inputs/weights/precision -- BASELINE.json's second baseline"}
+
+    if rank == 0 and args.impl == "ours":
+        try:
+            import bench_roofline
+            line.update(bench_roofline.measure(model, runner, dev_pool, device, world))
+        except Exception as exc:  # noqa: BLE001  -- the headline number must still print
+            line["roofline"] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg()
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": repr(exc)}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

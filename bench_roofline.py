@@ -1,0 +1,146 @@
+"""Roofline leg of bench.py: which of OUR kernels dominates the timed step, its algorithmic bytes (SURVEY.md
+section 8d formulas) over its device time measured live with CUDA events, against the measured HBM peak;
+plus the same figure for the four memory-bound ops at sweep sizes where they leave L2 (BASELINE.json
+configs[4]) and the FPS latency per iteration."""
+import json
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(name, a):
+    """SURVEY.md 8(d).  `a` = the integer arguments of the C-ABI call, in order."""
+    if name == "furthest_point_sampling":
+        b, n, m = a[:3]
+        return b * (12 * n + 4 * m)
+    if name in ("gather_points", "gather_points_grad"):
+        b, c, n, m = a[:4]
+        return b * (4 * c * min(n, m) + 4 * m + 4 * c * m) + (4 * b * c * n if name.endswith("grad") else 0)
+    if name == "ball_query":
+        b, n, m, ns = a[0], a[1], a[2], a[3]
+        return b * (12 * n + 12 * m + 4 * m * ns)
+    if name in ("group_points", "group_points_grad"):
+        b, c, n, m, ns = a[:5]
+        return b * (4 * c * min(n, m * ns) + 4 * m * ns + 4 * c * m * ns) + (4 * b * c * n if name.endswith("grad") else 0)
+    if name == "three_nn":
+        b, n, m = a[:3]
+        return b * (12 * n + 12 * m + 24 * n)
+    if name == "three_interpolate":
+        b, c, m, n = a[:4]
+        return b * (4 * c * min(m, 3 * n) + 24 * n + 4 * c * n)
+    if name == "three_interpolate_grad":
+        b, c, n, m = a[:4]
+        return b * (4 * c * min(m, 3 * n) + 24 * n + 4 * c * n) + 4 * b * c * m
+    if name.startswith("grid_gather_bilinear"):
+        b, c, h, w, n = a[:5]
+        return b * (4 * c * min(h * w, 4 * n) + 8 * n + 4 * c * n)
+    return a[-1] if a else 0  # fused kernels pass their own byte count last
+
+
+def _event_time(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3  # seconds
+
+
+def sweep_rooflines(device, peak):
+    """Memory-bound ops at sizes whose output alone exceeds L2 (126 MB), B=1."""
+    from epnet_b200 import pointnet2_cuda as pc
+    g = torch.Generator(device="cpu").manual_seed(0)
+    rows = []
+
+    def add(name, ints, fn):
+        t = _event_time(fn)
+        by = algorithmic_bytes(name, ints)
+        rows.append({"op": name, "shape": list(ints), "us": round(t * 1e6, 1), "algorithmic_mb": round(by / 1e6, 1),
+                     "achieved_gbs": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak, 3)})
+
+    C, N, M, ns = 128, 65536, 16384, 32
+    pts = torch.randn(1, C, N, device=device)
+    idx = torch.randint(0, N, (1, M, ns), generator=g).int().to(device)
+    out = torch.empty(1, C, M, ns, device=device)
+    add("group_points", (1, C, N, M, ns), lambda: pc.group_points_wrapper(1, C, N, M, ns, pts, idx, out))
+    gp = torch.zeros(1, C, N, device=device)
+    add("group_points_grad", (1, C, N, M, ns), lambda: pc.group_points_grad_wrapper(1, C, N, M, ns, out, idx, gp))
+    C, N, M = 512, 131072, 65536
+    pts = torch.randn(1, C, N, device=device)
+    gidx = torch.randint(0, N, (1, M), generator=g).int().to(device)
+    out = torch.empty(1, C, M, device=device)
+    add("gather_points", (1, C, N, M), lambda: pc.gather_points_wrapper(1, C, N, M, pts, gidx, out))
+    C, m, n = 256, 32768, 131072
+    pts = torch.randn(1, C, m, device=device)
+    idx3 = torch.randint(0, m, (1, n, 3), generator=g).int().to(device)
+    w = torch.rand(1, n, 3, generator=g).to(device)
+    out = torch.empty(1, C, n, device=device)
+    add("three_interpolate", (1, C, m, n), lambda: pc.three_interpolate_wrapper(1, C, m, n, pts, idx3, w, out))
+    C, H, W, n = 128, 384, 1280, 131072
+    fmap = torch.randn(1, C, H, W, device=device)
+    xy = (torch.rand(1, n, 2, generator=g) * 2 - 1).to(device)
+    out = torch.empty(1, C, n, device=device)
+    add("grid_gather_bilinear", (1, C, H, W, n), lambda: pc.grid_gather_bilinear_wrapper(1, C, H, W, n, fmap, xy, False, out))
+    return rows
+
+
+def measure(model, runner, dev_pool, device, world):
+    from epnet_b200 import pointnet2_cuda as pc
+    peak, peak_src = hbm_peak()
+    # instrumented EAGER passes of the same step: CUDA events around every C-ABI launch on its own stream
+    reps = 3
+    pc.PROFILE = []
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        s.record()
+        for r in range(reps):
+            b = dev_pool[r % len(dev_pool)]
+            if runner is not None:
+                runner.eager(b["points"], b["image"], b["xy"].clone())
+            else:
+                model(b["points"], b["image"], b["xy"].clone())
+        e.record()
+    torch.cuda.synchronize()
+    prof, pc.PROFILE = pc.PROFILE, None
+    step_ms = s.elapsed_time(e) / reps
+    agg = {}
+    for name, ints, e0, e1 in prof:
+        key = (name, tuple(ints))
+        t = e0.elapsed_time(e1) * 1e-3
+        tot, cnt = agg.get(key, (0.0, 0))
+        agg[key] = (tot + t, cnt + 1)
+    ranked = sorted(agg.items(), key=lambda kv: -kv[1][0])
+    kernels = [{"kernel": k[0], "args": list(k[1]), "launches_per_step": v[1] // reps, "us_per_launch": round(v[0] / v[1] * 1e6, 2),
+                "share_of_eager_step": round(v[0] / reps / (step_ms * 1e-3), 4)} for k, v in ranked[:12]]
+    (top_name, top_ints), (top_t, top_cnt) = ranked[0]
+    per_launch = top_t / top_cnt
+    by = algorithmic_bytes(top_name, top_ints)
+    out = {
+        "roofline": {"bound": "hbm", "kernel": top_name, "args": list(top_ints), "achieved": round(by / per_launch / 1e9, 3),
+                     "peak": peak, "unit": "GB/s", "frac": round(by / per_launch / 1e9 / peak, 5), "traffic": None,
+                     "peak_source": peak_src, "us_per_launch": round(per_launch * 1e6, 2), "algorithmic_bytes": by,
+                     "note": "dominant product kernel of the step by device time (events around each launch, eager pass)"},
+        "kernel_breakdown": kernels,
+        "eager_step_ms": round(step_ms, 3),
+    }
+    fps = [(k, v) for k, v in agg.items() if k[0].startswith("furthest_point_sampling")]
+    if fps:
+        out["fps_ns_per_iteration"] = {"%d->%d" % (k[1][1], k[1][2]): round(v[0] / v[1] / max(k[1][2] - 1, 1) * 1e9, 1) for k, v in fps}
+    if world == 1:
+        out["op_rooflines"] = sweep_rooflines(device, peak)
+    return out

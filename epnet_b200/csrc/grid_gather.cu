@@ -24,23 +24,23 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int 
 {
     float ix, iy;
     if (align_corners) {
-        ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
-        iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
-    } else {
-        ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
-        iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+        ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(w - 1));
+        iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(h - 1));
+    } else {  // ((x+1)*W - 1)/2 with the multiply-add contracted, as nvcc does for ATen's expression
+        ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), (float)w, -1.f), 0.5f);
+        iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), (float)h, -1.f), 0.5f);
     }
     const float fx = floorf(ix), fy = floorf(iy);
     const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
-    const float wx1 = ix - fx, wy1 = iy - fy;           // distance to the west / north corner
-    const float wx0 = (float)x1 - ix, wy0 = (float)y1 - iy;
+    const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);  // distance to the west / north corner
+    const float wx0 = __fsub_rn((float)x1, ix), wy0 = __fsub_rn((float)y1, iy);
     const bool xin0 = x0 >= 0 && x0 < w, xin1 = x1 >= 0 && x1 < w;
     const bool yin0 = y0 >= 0 && y0 < h, yin1 = y1 >= 0 && y1 < h;
     Taps t;
-    t.w[0] = (xin0 && yin0) ? wx0 * wy0 : 0.f;
-    t.w[1] = (xin1 && yin0) ? wx1 * wy0 : 0.f;
-    t.w[2] = (xin0 && yin1) ? wx0 * wy1 : 0.f;
-    t.w[3] = (xin1 && yin1) ? wx1 * wy1 : 0.f;
+    t.w[0] = (xin0 && yin0) ? __fmul_rn(wx0, wy0) : 0.f;
+    t.w[1] = (xin1 && yin0) ? __fmul_rn(wx1, wy0) : 0.f;
+    t.w[2] = (xin0 && yin1) ? __fmul_rn(wx0, wy1) : 0.f;
+    t.w[3] = (xin1 && yin1) ? __fmul_rn(wx1, wy1) : 0.f;
     t.o[0] = (xin0 && yin0) ? y0 * w + x0 : 0;
     t.o[1] = (xin1 && yin0) ? y0 * w + x1 : 0;
     t.o[2] = (xin0 && yin1) ? y1 * w + x0 : 0;
@@ -65,10 +65,10 @@ grid_gather_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, c
 #pragma unroll 4
     for (int ch = c_begin; ch < c_end; ++ch) {
         const float *p = fmap + (size_t)ch * plane;
-        float acc = __ldg(p + t.o[0]) * t.w[0];
-        acc += __ldg(p + t.o[1]) * t.w[1];
-        acc += __ldg(p + t.o[2]) * t.w[2];
-        acc += __ldg(p + t.o[3]) * t.w[3];
+        float acc = __fmul_rn(__ldg(p + t.o[0]), t.w[0]);
+        acc = __fmaf_rn(__ldg(p + t.o[1]), t.w[1], acc);
+        acc = __fmaf_rn(__ldg(p + t.o[2]), t.w[2], acc);
+        acc = __fmaf_rn(__ldg(p + t.o[3]), t.w[3], acc);
         out[(size_t)ch * n + i] = acc;
     }
 }

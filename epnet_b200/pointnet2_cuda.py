@@ -30,101 +30,95 @@ def _i(t, name):
     return _dev_ptr(t, torch.int32, name)
 
 
-def _stream(t):
-    # current stream of the tensor's device, like THCState_getCurrentStream in the reference wrappers;
-    # the device is made current so launches land on it even from a thread that never set it.
-    return torch.cuda.current_stream(t.device).cuda_stream
+LAUNCHES = [0]   # kernels launched through this module since it was last reset (bench.py's gpu_launches)
+PROFILE = None   # set to a list to record (name, int args, start_event, end_event) around every launch
 
 
-class _on:
-    """device guard: the reference relies on the caller having selected the device; we do it."""
-
-    def __init__(self, t):
-        self.guard = torch.cuda.device(t.device)
-
-    def __enter__(self):
-        self.guard.__enter__()
-
-    def __exit__(self, *a):
-        return self.guard.__exit__(*a)
+def _call(name, fn, ref, *args):
+    """Launch `fn(*args, stream)` on the current stream of `ref`'s device.  The reference wrappers rely on the
+    caller having selected the device (sampling.cpp:17); here it is selected when it is not current."""
+    device = ref.device
+    guard = None
+    if torch.cuda.current_device() != device.index:
+        guard = torch.cuda.device(device)
+        guard.__enter__()
+    try:
+        stream = torch.cuda.current_stream(device)
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            code = fn(*args, stream.cuda_stream)
+            e1.record(stream)
+            PROFILE.append((name, tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 31)), e0, e1))
+        else:
+            code = fn(*args, stream.cuda_stream)
+    finally:
+        if guard is not None:
+            guard.__exit__(None, None, None)
+    LAUNCHES[0] += 1
+    check(code, name)
 
 
 def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
-    with _on(points_tensor):
-        check(LIB.epnet_furthest_point_sampling(b, n, m, _f(points_tensor, "xyz"), _f(temp_tensor, "temp"),
-                                                _i(idx_tensor, "idx"), _stream(points_tensor)),
-              "furthest_point_sampling")
+    _call("furthest_point_sampling", LIB.epnet_furthest_point_sampling, points_tensor, b, n, m, _f(points_tensor, "xyz"),
+          _f(temp_tensor, "temp"), _i(idx_tensor, "idx"))
     return 1
 
 
 def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tensor):
-    with _on(points_tensor):
-        check(LIB.epnet_gather_points(b, c, n, npoints, _f(points_tensor, "points"), _i(idx_tensor, "idx"),
-                                      _f(out_tensor, "out"), _stream(points_tensor)), "gather_points")
+    _call("gather_points", LIB.epnet_gather_points, points_tensor, b, c, n, npoints, _f(points_tensor, "points"),
+          _i(idx_tensor, "idx"), _f(out_tensor, "out"))
     return 1
 
 
 def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, grad_points_tensor):
-    with _on(grad_out_tensor):
-        check(LIB.epnet_gather_points_grad(b, c, n, npoints, _f(grad_out_tensor, "grad_out"), _i(idx_tensor, "idx"),
-                                           _f(grad_points_tensor, "grad_points"), _stream(grad_out_tensor)),
-              "gather_points_grad")
+    _call("gather_points_grad", LIB.epnet_gather_points_grad, grad_out_tensor, b, c, n, npoints,
+          _f(grad_out_tensor, "grad_out"), _i(idx_tensor, "idx"), _f(grad_points_tensor, "grad_points"))
     return 1
 
 
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
-    with _on(xyz_tensor):
-        check(LIB.epnet_ball_query(b, n, m, float(radius), nsample, _f(new_xyz_tensor, "new_xyz"), _f(xyz_tensor, "xyz"),
-                                   _i(idx_tensor, "idx"), _stream(xyz_tensor)), "ball_query")
+    _call("ball_query", LIB.epnet_ball_query, xyz_tensor, b, n, m, float(radius), nsample, _f(new_xyz_tensor, "new_xyz"),
+          _f(xyz_tensor, "xyz"), _i(idx_tensor, "idx"))
     return 1
 
 
 def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, out_tensor):
-    with _on(points_tensor):
-        check(LIB.epnet_group_points(b, c, n, npoints, nsample, _f(points_tensor, "points"), _i(idx_tensor, "idx"),
-                                     _f(out_tensor, "out"), _stream(points_tensor)), "group_points")
+    _call("group_points", LIB.epnet_group_points, points_tensor, b, c, n, npoints, nsample, _f(points_tensor, "points"),
+          _i(idx_tensor, "idx"), _f(out_tensor, "out"))
     return 1
 
 
 def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor, grad_points_tensor):
-    with _on(grad_out_tensor):
-        check(LIB.epnet_group_points_grad(b, c, n, npoints, nsample, _f(grad_out_tensor, "grad_out"),
-                                          _i(idx_tensor, "idx"), _f(grad_points_tensor, "grad_points"),
-                                          _stream(grad_out_tensor)), "group_points_grad")
+    _call("group_points_grad", LIB.epnet_group_points_grad, grad_out_tensor, b, c, n, npoints, nsample,
+          _f(grad_out_tensor, "grad_out"), _i(idx_tensor, "idx"), _f(grad_points_tensor, "grad_points"))
     return 1
 
 
 def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
-    with _on(unknown_tensor):
-        check(LIB.epnet_three_nn(b, n, m, _f(unknown_tensor, "unknown"), _f(known_tensor, "known"),
-                                 _f(dist2_tensor, "dist2"), _i(idx_tensor, "idx"), _stream(unknown_tensor)), "three_nn")
+    _call("three_nn", LIB.epnet_three_nn, unknown_tensor, b, n, m, _f(unknown_tensor, "unknown"), _f(known_tensor, "known"),
+          _f(dist2_tensor, "dist2"), _i(idx_tensor, "idx"))
 
 
 def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
-    with _on(points_tensor):
-        check(LIB.epnet_three_interpolate(b, c, m, n, _f(points_tensor, "points"), _i(idx_tensor, "idx"),
-                                          _f(weight_tensor, "weight"), _f(out_tensor, "out"), _stream(points_tensor)),
-              "three_interpolate")
+    _call("three_interpolate", LIB.epnet_three_interpolate, points_tensor, b, c, m, n, _f(points_tensor, "points"),
+          _i(idx_tensor, "idx"), _f(weight_tensor, "weight"), _f(out_tensor, "out"))
 
 
 def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
-    with _on(grad_out_tensor):
-        check(LIB.epnet_three_interpolate_grad(b, c, n, m, _f(grad_out_tensor, "grad_out"), _i(idx_tensor, "idx"),
-                                               _f(weight_tensor, "weight"), _f(grad_points_tensor, "grad_points"),
-                                               _stream(grad_out_tensor)), "three_interpolate_grad")
+    _call("three_interpolate_grad", LIB.epnet_three_interpolate_grad, grad_out_tensor, b, c, n, m,
+          _f(grad_out_tensor, "grad_out"), _i(idx_tensor, "idx"), _f(weight_tensor, "weight"),
+          _f(grad_points_tensor, "grad_points"))
 
 
 # ---- LI-Fusion gather (not part of the reference's pybind table; see epnet_b200.li_fusion) ----
 
 def grid_gather_bilinear_wrapper(b, c, h, w, n, fmap_tensor, xy_tensor, align_corners, out_tensor):
-    with _on(fmap_tensor):
-        check(LIB.epnet_grid_gather_bilinear(b, c, h, w, n, _f(fmap_tensor, "feature_map"), _f(xy_tensor, "xy"),
-                                             int(bool(align_corners)), _f(out_tensor, "out"), _stream(fmap_tensor)),
-              "grid_gather_bilinear")
+    _call("grid_gather_bilinear", LIB.epnet_grid_gather_bilinear, fmap_tensor, b, c, h, w, n, _f(fmap_tensor, "feature_map"),
+          _f(xy_tensor, "xy"), int(bool(align_corners)), _f(out_tensor, "out"))
 
 
 def grid_gather_bilinear_grad_wrapper(b, c, h, w, n, grad_out_tensor, xy_tensor, align_corners, grad_fmap_tensor):
-    with _on(grad_out_tensor):
-        check(LIB.epnet_grid_gather_bilinear_grad(b, c, h, w, n, _f(grad_out_tensor, "grad_out"), _f(xy_tensor, "xy"),
-                                                  int(bool(align_corners)), _f(grad_fmap_tensor, "grad_feature_map"),
-                                                  _stream(grad_out_tensor)), "grid_gather_bilinear_grad")
+    _call("grid_gather_bilinear_grad", LIB.epnet_grid_gather_bilinear_grad, grad_out_tensor, b, c, h, w, n,
+          _f(grad_out_tensor, "grad_out"), _f(xy_tensor, "xy"), int(bool(align_corners)),
+          _f(grad_fmap_tensor, "grad_feature_map"))

@@ -124,7 +124,8 @@ class Atten_Fusion_Conv(nn.Module):
 class Pointnet2MSG(nn.Module):
     """RPN backbone (pointnet2_msg.py:127-248)."""
 
-    def __init__(self, input_channels=None, use_xyz=None, config: BackboneConfig = None, ops=None, feature_gather=None):
+    def __init__(self, input_channels=None, use_xyz=None, config: BackboneConfig = None, ops=None, feature_gather=None,
+                 reference_composition=False):
         super().__init__()
         c = config or BackboneConfig()
         if input_channels is not None:
@@ -132,6 +133,8 @@ class Pointnet2MSG(nn.Module):
         if use_xyz is not None:
             c.use_xyz = use_xyz
         self.config = c
+        # True: always run the reference's op-by-op composition (no fused kernels, no CUDA graph)
+        self.reference_composition = reference_composition
         self._ops = ops or pointnet2_utils.OPS
         # (feature_map (B,C,H,W), xy (B,N,2)) -> (B,C,N); the LI-Fusion boundary
         self._feature_gather = feature_gather or (lambda fm, xy: li_fusion.feature_gather(fm, xy, c.align_corners))

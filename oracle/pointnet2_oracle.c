@@ -229,7 +229,9 @@ ORACLE_API void oracle_three_interpolate_grad(int b, int c, int n, int m, const 
  *   align_corners: ix = (x+1)/2*(W-1)      else: ix = ((x+1)*W-1)/2
  * floor to the NW corner, weights nw=(ixe-ix)(iye-iy) ..., out-of-range taps contribute zero,
  * taps summed in the order nw, ne, sw, se.  Anchored on torch's own CPU grid_sample in
- * tests/test_oracle.py (<=1e-6 abs); float, not bit-exact. */
+ * tests/test_oracle.py; float, not bit-exact.  Where device code contracts a multiply-add into one FMA
+ * the same FMA is written out here, so that CPU and GPU agree to the last bits on the sampling position
+ * (a 1-ulp difference in a pixel coordinate of ~1000 would otherwise show up as ~1e-4 in the output). */
 ORACLE_API void oracle_grid_gather_bilinear(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out)
 {
     #pragma omp parallel for collapse(2) schedule(static)
@@ -243,9 +245,9 @@ ORACLE_API void oracle_grid_gather_bilinear(int b, int c, int h, int w, int n, c
                 if (align_corners) {
                     ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
                     iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
-                } else {
-                    ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
-                    iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+                } else { /* (x+1)*W-1 contracts to one FMA in device code (nvcc -fmad=true, ATen's build too) */
+                    ix = fmaf(gx + 1.f, (float)w, -1.f) / 2.f;
+                    iy = fmaf(gy + 1.f, (float)h, -1.f) / 2.f;
                 }
                 const float fx = floorf(ix), fy = floorf(iy);
                 const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
@@ -253,11 +255,11 @@ ORACLE_API void oracle_grid_gather_bilinear(int b, int c, int h, int w, int n, c
                 const float wne = (ix - (float)x0) * ((float)y1 - iy);
                 const float wsw = ((float)x1 - ix) * (iy - (float)y0);
                 const float wse = (ix - (float)x0) * (iy - (float)y0);
-                float acc = 0.f;
-                if (x0 >= 0 && x0 < w && y0 >= 0 && y0 < h) acc += img[(size_t)y0 * w + x0] * wnw;
-                if (x1 >= 0 && x1 < w && y0 >= 0 && y0 < h) acc += img[(size_t)y0 * w + x1] * wne;
-                if (x0 >= 0 && x0 < w && y1 >= 0 && y1 < h) acc += img[(size_t)y1 * w + x0] * wsw;
-                if (x1 >= 0 && x1 < w && y1 >= 0 && y1 < h) acc += img[(size_t)y1 * w + x1] * wse;
+                float acc = 0.f; /* acc += v*w is one FMA per tap in device code */
+                if (x0 >= 0 && x0 < w && y0 >= 0 && y0 < h) acc = fmaf(img[(size_t)y0 * w + x0], wnw, acc);
+                if (x1 >= 0 && x1 < w && y0 >= 0 && y0 < h) acc = fmaf(img[(size_t)y0 * w + x1], wne, acc);
+                if (x0 >= 0 && x0 < w && y1 >= 0 && y1 < h) acc = fmaf(img[(size_t)y1 * w + x0], wsw, acc);
+                if (x1 >= 0 && x1 < w && y1 >= 0 && y1 < h) acc = fmaf(img[(size_t)y1 * w + x1], wse, acc);
                 dst[j] = acc;
             }
         }
@@ -276,9 +278,9 @@ ORACLE_API void oracle_grid_gather_bilinear_grad(int b, int c, int h, int w, int
                 if (align_corners) {
                     ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
                     iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
-                } else {
-                    ix = ((gx + 1.f) * (float)w - 1.f) / 2.f;
-                    iy = ((gy + 1.f) * (float)h - 1.f) / 2.f;
+                } else { /* (x+1)*W-1 contracts to one FMA in device code (nvcc -fmad=true, ATen's build too) */
+                    ix = fmaf(gx + 1.f, (float)w, -1.f) / 2.f;
+                    iy = fmaf(gy + 1.f, (float)h, -1.f) / 2.f;
                 }
                 const float fx = floorf(ix), fy = floorf(iy);
                 const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
