@@ -1,146 +1,390 @@
 // Furthest point sampling for B200.  Replaces furthest_point_sampling_kernel
 // (/root/reference/pointnet2_lib/pointnet2/src/sampling_gpu.cu:93-209) bit-exactly.
 //
-// What has to be reproduced: every iteration j picks arg-max over k of temp[k] = min(temp[k], d(k, last)).
+// What has to be reproduced: iteration j picks arg-max over k of temp[k] = min(temp[k], d(k, last)).
 // The reference resolves equal maxima through (a) a strided per-thread scan that keeps the first
 // maximum and (b) a shared-memory tree that keeps the lower slot unless the upper is strictly larger.
-// The net effect is: among tied k the winner minimises  tie(k) = (bitreverse_L(k mod BS), k div BS),
-// BS = 2^L = min(1024, 2^floor(log2 N))  (cuda_utils.h:10-14).  We compute that order directly:
-// a candidate is the pair (distance bits, tie key); distances are >= 0 so their IEEE bits order as
-// unsigned ints, and the winner is  max distance, then min tie key -- two warp `redux.sync`
-// instructions per level instead of a 10-barrier shared-memory tree.
+// Net effect: among tied k the winner minimises  (bitreverse_L(k mod BS), k div BS),
+// BS = 2^L = min(1024, 2^floor(log2 N))  (cuda_utils.h:10-14).  We compute that order directly: a
+// candidate is (distance bits, tie word); distances are >= 0 so their IEEE bits order as unsigned
+// ints; the winner is max distance, then min tie word -- two warp `redux.sync` per level instead of
+// a 10-barrier shared-memory tree.
 //
-// Layout (resident variant, N <= 16384): one CTA per scene, BS threads; coordinates are transposed once
-// into shared memory as three float planes (192 KB at N=16384, conflict-free: lane l reads word l), the
-// running distances live in registers (thread t owns points t, t+BS, ...: the reference's ownership, so
-// its "first maximum per thread" rule carries over unchanged).  One __syncthreads per iteration:
-// warp winners go to a double-buffered slot array that every warp re-reduces for itself.
-// Streaming variant (N > 16384): same reduction, coordinates and temp stay in global memory / L2.
+// The reference does N distance updates per iteration (M*N in total, 67 M for 16384->4096) on one
+// SM.  Here the work per iteration is made proportional to the points that can actually change:
+//   * points are counting-sorted once, in shared memory, into Morton order of a near-cubic cell grid;
+//     128 consecutive sorted points form a bucket with an exact bounding box;
+//   * each bucket caches its current (max running distance, tie word);
+//   * an iteration first tests the new sample against every bucket's box: if the (slightly deflated)
+//     box distance is >= the bucket's max running distance, no min() in that bucket can change, its
+//     cached winner stays valid and the bucket is skipped -- which is what happens to almost all
+//     buckets once a few dozen samples exist.  Skipping never changes a result: every distance that
+//     IS computed uses the reference's exact FMA sequence, every skipped one is provably >= temp.
+// Sorted coordinates live in shared memory as three planes (192 KB at N = 16384), running distances and
+// tie words in registers (lane l of warp w owns sorted positions (((b*NW+w)*kSlots+i)*32+l), bucket boxes and
+// cached winners in the registers of lanes 0..7.  One __syncthreads per iteration (none when a single
+// warp holds the whole cloud, N <= 1024).  N > 16384 streams from L2 (fps_streaming_kernel).
 #include "common.cuh"
 
 namespace epnet {
 
 constexpr int kFpsMaxResident = 16384;  // 3 planes * 4 B * 16384 = 192 KB of the 227 KB shared memory
+constexpr int kBuckets = 8;             // buckets per warp
+constexpr float kBoxDeflate = 0.999996f;  // > (1 - 2^-18): covers the few-ulp rounding of both distance evaluations
 
 struct FpsCand {
     uint32_t dist_bits;
     uint32_t tie;
 };
 
-__device__ __forceinline__ uint32_t fps_tie_key(uint32_t k, uint32_t tid, int L)
+// ---- tie words -------------------------------------------------------------------------------
+// compact key ck(k) = (bitreverse_L(k mod BS) << qbits) | (k >> L)   (order == the reference's tie order)
+// tie word = (ck << 16) | sorted position            (N <= 16384: ck < 2^14, position < 2^14)
+__device__ __forceinline__ uint32_t fps_compact_key(uint32_t k, int L, int qbits)
 {
-    // tid < 2^L so __brev(tid) occupies the top L bits; k >> L < 2^(32-L).
-    return __brev(tid) | (k >> L);
+    const uint32_t rev = L ? (__brev(k & ((1u << L) - 1u)) >> (32 - L)) : 0u;
+    return (rev << qbits) | (k >> L);
 }
-__device__ __forceinline__ uint32_t fps_tie_decode(uint32_t tie, int L)
+__device__ __forceinline__ uint32_t fps_key_to_index(uint32_t ck, int L, int qbits)
 {
-    const uint32_t low = L ? (0xffffffffu >> L) : 0xffffffffu;
-    const uint32_t tid = __brev(tie & ~low);
-    return ((tie & low) << L) | tid;
-}
-
-// Block-wide arg-max with the reference's tie rule.  Returns the winning point index to every thread.
-// slots: 2 * 32 entries, parity flips per call so one barrier per call is enough.
-__device__ __forceinline__ uint32_t fps_block_argmax(uint32_t dist_bits, uint32_t tie, FpsCand *slots, int parity, int nwarps, int L)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t mx = warp_max_u32(dist_bits);
-    uint32_t mt = warp_min_u32(dist_bits == mx ? tie : 0xffffffffu);
-    if (nwarps > 1) {
-        FpsCand *s = slots + parity * 32;
-        if (lane == 0) {
-            s[warp].dist_bits = mx;
-            s[warp].tie = mt;
-        }
-        __syncthreads();
-        FpsCand c;
-        c.dist_bits = 0u;
-        c.tie = 0xffffffffu;
-        if (lane < nwarps) c = s[lane];
-        mx = warp_max_u32(c.dist_bits);
-        mt = warp_min_u32(c.dist_bits == mx ? c.tie : 0xffffffffu);
-    }
-    return fps_tie_decode(mt, L);
+    const uint32_t hi = ck & ((1u << qbits) - 1u);
+    const uint32_t rev = ck >> qbits;
+    const uint32_t low = L ? (__brev(rev) >> (32 - L)) : 0u;
+    return (hi << L) | low;
 }
 
-template <int P>
-__global__ void __launch_bounds__(1024, 1)
-fps_resident_kernel(int n, int m, int L, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx)
+__device__ __forceinline__ float warp_min_f(float v)
 {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// (max distance bits, then min tie word) over the warp
+__device__ __forceinline__ void warp_argmax(uint32_t &bits, uint32_t &tie)
+{
+    const uint32_t mx = warp_max_u32(bits);
+    tie = warp_min_u32(bits == mx ? tie : 0xffffffffu);
+    bits = mx;
+}
+
+// NW warps, kBuckets buckets per warp, kSlots points per lane per bucket (bucket = 32*kSlots sorted points).
+// Buckets are dealt to warps round-robin (bucket g -> warp g % NW): buckets that are neighbours in Morton
+// order, i.e. the ones a new sample touches together, are updated by different warps in parallel.
+template <int NW, int kSlots>
+__global__ void __launch_bounds__(NW * 32, 1)
+fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx)
+{
+    constexpr int T = NW * 32;
+    constexpr int CAP = T * kBuckets * kSlots;  // sorted positions this CTA can hold
+    constexpr int PPT = CAP / T;                // points per thread during the sort
+    constexpr int NCELL = CAP;                  // one cell per sorted position on average; the histogram aliases one plane
+    constexpr int CB = NW == 1 ? (kSlots == 1 ? 8 : 10) : NW == 4 ? (kSlots == 1 ? 10 : 12) : (kSlots == 1 ? 12 : 14);
+    static_assert((1 << CB) == NCELL, "cell bits");
+#define FPS_POS(b, i) ((((b) * NW + warp) * kSlots + (i)) * 32 + lane)
+
     extern __shared__ __align__(16) float fps_smem[];
-    __shared__ FpsCand slots[64];
-    float *xs = fps_smem, *ys = fps_smem + n, *zs = fps_smem + 2 * n;
+    float *xs = fps_smem, *ys = fps_smem + CAP, *zs = fps_smem + 2 * CAP;
+    // aliases used before the planes are filled
+    uint32_t *hist = reinterpret_cast<uint32_t *>(fps_smem);             // NCELL counters
+    float *carry_t = fps_smem;                                            // CAP running distances by sorted position
+    uint32_t *carry_k = reinterpret_cast<uint32_t *>(fps_smem + CAP);     // CAP original indices by sorted position
+
+    __shared__ float red[32][6];
+    __shared__ float box[6];          // scene bounding box: min xyz, max xyz
+    __shared__ float inv_cell[3];
+    __shared__ int axis_bits[3];
+    __shared__ int bit_axis[16];      // axis providing Morton bit s (MSB first)
+    __shared__ uint32_t warp_tot[32];
+    __shared__ FpsCand slots[2][32];
 
     const int scene = blockIdx.x;
     xyz += (size_t)scene * n * 3;
     temp += (size_t)scene * n;
     idx += (size_t)scene * m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float inf = __int_as_float(0x7f800000);
 
-    const int tid = threadIdx.x;
-    const int bs = 1 << L;
-    const int nthreads = blockDim.x;  // max(bs, 32)
-    const int nwarps = nthreads >> 5;
-
-    // transpose (N,3) -> three planes; the flat read is fully coalesced
-    for (int f = tid; f < 3 * n; f += nthreads) {
-        const int p = f / 3, c = f - 3 * p;
-        fps_smem[c * n + p] = xyz[f];
-    }
-    float t[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const int k = tid + i * bs;
-        t[i] = (tid < bs && k < n) ? temp[k] : 0.f;
-    }
     if (tid == 0) idx[0] = 0;
+    if (m == 1) return;
+
+    // ---------------- 1. scene bounding box ----------------
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * T;
+        if (k < n) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(xyz + 3 * k + a);
+                lo[a] = fminf(lo[a], v);
+                hi[a] = fmaxf(hi[a], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = warp_min_f(lo[a]);
+        hi[a] = warp_max_f(hi[a]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            red[warp][a] = lo[a];
+            red[warp][3 + a] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ext[3];
+        for (int a = 0; a < 3; ++a) {
+            float l = inf, h = -inf;
+            for (int w = 0; w < NW; ++w) {
+                l = fminf(l, red[w][a]);
+                h = fmaxf(h, red[w][3 + a]);
+            }
+            box[a] = l;
+            box[3 + a] = h;
+            ext[a] = (h > l && h - l < inf) ? h - l : 0.f;  // empty / degenerate / non-finite axes get no bits
+            axis_bits[a] = 0;
+        }
+        // hand out CB Morton bits, MSB first, always to the axis whose cells are currently longest
+        float cell[3] = {ext[0], ext[1], ext[2]};
+        for (int s = 0; s < CB; ++s) {
+            int best = 0;
+            if (cell[2] > cell[best]) best = 2;   // prefer x, then z, then y on ties
+            if (cell[1] > cell[best]) best = 1;
+            bit_axis[s] = best;
+            axis_bits[best] += 1;
+            cell[best] *= 0.5f;
+        }
+        for (int a = 0; a < 3; ++a) inv_cell[a] = ext[a] > 0.f ? (float)(1 << axis_bits[a]) / ext[a] : 0.f;
+    }
+    for (int c = tid; c < NCELL; c += T) hist[c] = 0u;
     __syncthreads();
 
-    uint32_t last = 0;
-    for (int j = 1; j < m; ++j) {
-        const float lx = xs[last], ly = ys[last], lz = zs[last];
-        float best = -1.f;
-        uint32_t besti = 0;
-        if (tid < bs) {
+    // ---------------- 2. cell of every point, rank inside the cell ----------------
+    // cell | rank << CB, later the sorted position.  Indexed dynamically on purpose (not unrolled): it lives in
+    // local memory (L1), is touched four times per point in this one-off prologue, and keeps the code small.
+    uint32_t code[PPT];
+    {
+        const int nb0 = axis_bits[0], nb1 = axis_bits[1], nb2 = axis_bits[2];
+        const float bx = box[0], by = box[1], bz = box[2];
+        const float ix = inv_cell[0], iy = inv_cell[1], iz = inv_cell[2];
+#pragma unroll 1
+        for (int i = 0; i < PPT; ++i) {
+            const int k = tid + i * T;
+            code[i] = 0xffffffffu;
+            if (k < n) {
+                const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+                int q[3];
+                q[0] = min(max((int)((x - bx) * ix), 0), (1 << nb0) - 1);   // NaN -> 0
+                q[1] = min(max((int)((y - by) * iy), 0), (1 << nb1) - 1);
+                q[2] = min(max((int)((z - bz) * iz), 0), (1 << nb2) - 1);
+                int left[3] = {nb0, nb1, nb2};
+                uint32_t cell = 0;
+                for (int s = 0; s < CB; ++s) {
+                    const int a = bit_axis[s];
+                    const int l = (a == 0 ? left[0] : (a == 1 ? left[1] : left[2])) - 1;
+                    const int qa = a == 0 ? q[0] : (a == 1 ? q[1] : q[2]);
+                    cell = (cell << 1) | ((qa >> l) & 1);
+                    if (a == 0) left[0] = l; else if (a == 1) left[1] = l; else left[2] = l;
+                }
+                const uint32_t rank = atomicAdd(&hist[cell], 1u);
+                code[i] = cell | (rank << CB);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- 3. exclusive scan of the histogram (PPT consecutive cells per thread) ----------------
+    {
+        uint32_t sum = 0;
+#pragma unroll 4
+        for (int i = 0; i < PPT; ++i) sum += hist[tid * PPT + ((i + lane) & (PPT - 1))];  // rotated: conflict-free
+        uint32_t incl = sum;
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const int k = tid + i * bs;
-                if (k < n) {
-                    const float d = sqdist_ref(xs[k], ys[k], zs[k], lx, ly, lz);
-                    const float d2 = fminf(d, t[i]);
-                    t[i] = d2;
-                    if (d2 > best) {
-                        best = d2;
-                        besti = k;
-                    }
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < warp; ++w) run += warp_tot[w];
+#pragma unroll 4
+        for (int i = 0; i < PPT; ++i) {
+            const uint32_t c = hist[tid * PPT + i];
+            hist[tid * PPT + i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < PPT; ++i)
+        if (code[i] != 0xffffffffu) code[i] = hist[code[i] & (NCELL - 1)] + (code[i] >> CB);  // sorted position
+    __syncthreads();
+
+    // ---------------- 4. carry running distance + original index to the owner of each sorted position ----------------
+#pragma unroll 1
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * T;
+        if (k < n) {
+            carry_t[code[i]] = temp[k];
+            carry_k[code[i]] = (uint32_t)k;
+        }
+    }
+    __syncthreads();
+    float t[kBuckets][kSlots];
+    uint32_t tw[kBuckets][kSlots];
+#pragma unroll
+    for (int b = 0; b < kBuckets; ++b)
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int pos = FPS_POS(b, i);
+            if (pos < n) {
+                t[b][i] = carry_t[pos];
+                tw[b][i] = (fps_compact_key(carry_k[pos], L, qbits) << 16) | (uint32_t)pos;
+            } else {  // empty slot: never changes, loses every tie
+                t[b][i] = 0.f;
+                tw[b][i] = 0xffffffffu;
+            }
+        }
+    __syncthreads();
+
+    // ---------------- 5. scatter coordinates into the sorted planes ----------------
+#pragma unroll 1
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * T;
+        if (k < n) {
+            const uint32_t pos = code[i];
+            xs[pos] = __ldg(xyz + 3 * k);
+            ys[pos] = __ldg(xyz + 3 * k + 1);
+            zs[pos] = __ldg(xyz + 3 * k + 2);
+        }
+    }
+    for (int pos = n + tid; pos < CAP; pos += T) xs[pos] = ys[pos] = zs[pos] = 0.f;
+    __syncthreads();
+
+    // ---------------- 6. bucket boxes and initial cached winners (lane b keeps bucket b) ----------------
+    float blo_x = inf, blo_y = inf, blo_z = inf, bhi_x = -inf, bhi_y = -inf, bhi_z = -inf;
+    uint32_t bmax = 0u, bkey = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kBuckets; ++b) {
+        float l0 = inf, l1 = inf, l2 = inf, h0 = -inf, h1 = -inf, h2 = -inf;
+        float bt = t[b][0];
+        uint32_t bk = tw[b][0];
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int pos = FPS_POS(b, i);
+            if (pos < n) {
+                const float x = xs[pos], y = ys[pos], z = zs[pos];
+                l0 = fminf(l0, x); h0 = fmaxf(h0, x);
+                l1 = fminf(l1, y); h1 = fmaxf(h1, y);
+                l2 = fminf(l2, z); h2 = fmaxf(h2, z);
+            }
+            if (i > 0) {
+                const bool take = (t[b][i] > bt) || (t[b][i] == bt && tw[b][i] < bk);
+                bt = take ? t[b][i] : bt;
+                bk = take ? tw[b][i] : bk;
+            }
+        }
+        l0 = warp_min_f(l0); l1 = warp_min_f(l1); l2 = warp_min_f(l2);
+        h0 = warp_max_f(h0); h1 = warp_max_f(h1); h2 = warp_max_f(h2);
+        uint32_t bits = __float_as_uint(bt);
+        warp_argmax(bits, bk);
+        if (lane == b) {
+            blo_x = l0; blo_y = l1; blo_z = l2;
+            bhi_x = h0; bhi_y = h1; bhi_z = h2;
+            bmax = bits; bkey = bk;
+        }
+    }
+
+    // ---------------- 7. the sampling loop ----------------
+    float cx = __ldg(xyz), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // sample 0 is point 0
+    for (int j = 1; j < m; ++j) {
+        // which buckets can change?  box distance (deflated) vs the bucket's largest running distance
+        const float ex = fmaxf(fmaxf(blo_x - cx, cx - bhi_x), 0.f);
+        const float ey = fmaxf(fmaxf(blo_y - cy, cy - bhi_y), 0.f);
+        const float ez = fmaxf(fmaxf(blo_z - cz, cz - bhi_z), 0.f);
+        const float lb = (ex * ex + ey * ey + ez * ez) * kBoxDeflate;
+        const bool active = lane < kBuckets && lb < __uint_as_float(bmax);
+        const uint32_t mask = __ballot_sync(0xffffffffu, active);
+#pragma unroll
+        for (int b = 0; b < kBuckets; ++b) {
+            if (mask & (1u << b)) {  // warp-uniform
+                float bt = 0.f;
+                uint32_t bk = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i) {
+                    const int pos = FPS_POS(b, i);
+                    const float d = sqdist_ref(xs[pos], ys[pos], zs[pos], cx, cy, cz);
+                    const float v = fminf(d, t[b][i]);
+                    t[b][i] = v;
+                    const bool take = (i == 0) || (v > bt) || (v == bt && tw[b][i] < bk);
+                    bt = take ? v : bt;
+                    bk = take ? tw[b][i] : bk;
+                }
+                uint32_t bits = __float_as_uint(bt);
+                warp_argmax(bits, bk);
+                if (lane == b) {
+                    bmax = bits;
+                    bkey = bk;
                 }
             }
         }
-        const bool has = tid < bs;  // every thread below bs owns point k = tid < n
-        last = fps_block_argmax(has ? __float_as_uint(best) : 0u, has ? fps_tie_key(besti, tid, L) : 0xffffffffu, slots, j & 1,
-                                nwarps, L);
-        if (tid == 0) idx[j] = (int)last;
+        // winner of the warp's 8 buckets, then of the CTA
+        uint32_t wbits = lane < kBuckets ? bmax : 0u;
+        uint32_t wkey = lane < kBuckets ? bkey : 0xffffffffu;
+        warp_argmax(wbits, wkey);
+        if (NW > 1) {
+            FpsCand *s = slots[j & 1];
+            if (lane == 0) {
+                s[warp].dist_bits = wbits;
+                s[warp].tie = wkey;
+            }
+            __syncthreads();
+            wbits = lane < NW ? s[lane].dist_bits : 0u;
+            wkey = lane < NW ? s[lane].tie : 0xffffffffu;
+            warp_argmax(wbits, wkey);
+        }
+        const uint32_t pos = wkey & 0xffffu;
+        cx = xs[pos];
+        cy = ys[pos];
+        cz = zs[pos];
+        if (tid == 0) idx[j] = (int)fps_key_to_index(wkey >> 16, L, qbits);
     }
 
-    // temp is an in/out buffer in the reference; leave the final running distances behind.
-    if (tid < bs) {
+    // temp is an in/out buffer in the reference: leave the final running distances behind
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            const int k = tid + i * bs;
-            if (k < n) temp[k] = t[i];
-        }
-    }
+    for (int b = 0; b < kBuckets; ++b)
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i)
+            if (tw[b][i] != 0xffffffffu) temp[fps_key_to_index(tw[b][i] >> 16, L, qbits)] = t[b][i];
 }
 
-// N too large for one SM's shared memory: coordinates and running distances stream from L2.
+// ---- N too large for one SM's shared memory: coordinates and running distances stream from L2 ----
+__device__ __forceinline__ uint32_t fps_tie_key(uint32_t k, uint32_t tid, int L) { return __brev(tid) | (k >> L); }
+__device__ __forceinline__ uint32_t fps_tie_decode(uint32_t tie, int L)
+{
+    const uint32_t low = L ? (0xffffffffu >> L) : 0xffffffffu;
+    return ((tie & low) << L) | __brev(tie & ~low);
+}
+
 __global__ void __launch_bounds__(1024, 1)
 fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx)
 {
-    __shared__ FpsCand slots[64];
+    __shared__ FpsCand slots[2][32];
     const int scene = blockIdx.x;
     xyz += (size_t)scene * n * 3;
     temp += (size_t)scene * n;
     idx += (size_t)scene * m;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int L = 10;
     if (tid == 0) idx[0] = 0;
 
@@ -149,7 +393,7 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
         const float lx = __ldg(xyz + 3 * last), ly = __ldg(xyz + 3 * last + 1), lz = __ldg(xyz + 3 * last + 2);
         float best = -1.f;
         uint32_t besti = 0;
-        for (int k = tid; k < n; k += 1024) {
+        for (int k = tid; k < n; k += 1024) {  // the reference's ownership: "first maximum per thread" carries over
             const float d = sqdist_ref(__ldg(xyz + 3 * k), __ldg(xyz + 3 * k + 1), __ldg(xyz + 3 * k + 2), lx, ly, lz);
             const float d2 = fminf(d, temp[k]);
             temp[k] = d2;
@@ -158,19 +402,29 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
                 besti = k;
             }
         }
-        last = fps_block_argmax(__float_as_uint(best), fps_tie_key(besti, tid, L), slots, j & 1, 32, L);
+        uint32_t bits = __float_as_uint(best), tie = fps_tie_key(besti, tid, L);
+        warp_argmax(bits, tie);
+        FpsCand *s = slots[j & 1];
+        if (lane == 0) {
+            s[warp].dist_bits = bits;
+            s[warp].tie = tie;
+        }
+        __syncthreads();
+        bits = s[lane].dist_bits;
+        tie = s[lane].tie;
+        warp_argmax(bits, tie);
+        last = fps_tie_decode(tie, L);
         if (tid == 0) idx[j] = (int)last;
     }
 }
 
-template <int P>
-static int launch_resident(int b, int n, int m, int L, const float *xyz, float *temp, int *idx, cudaStream_t st)
+template <int NW, int kSlots>
+static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, cudaStream_t st)
 {
-    const size_t smem = (size_t)3 * n * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fps_resident_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)3 * NW * 32 * kBuckets * kSlots * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<NW, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int threads = (1 << L) < 32 ? 32 : (1 << L);
-    fps_resident_kernel<P><<<b, threads, smem, st>>>(n, m, L, xyz, temp, idx);
+    fps_bucket_kernel<NW, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
@@ -185,12 +439,13 @@ EPNET_API int epnet_furthest_point_sampling(int b, int n, int m, const float *xy
     int L = 0;
     while ((2 << L) <= n && L < 10) ++L;  // BS = 2^L = min(1024, 2^floor(log2 n))
     if (n <= kFpsMaxResident) {
-        const int per = (n + (1 << L) - 1) >> L;
-        if (per <= 1) return launch_resident<1>(b, n, m, L, xyz, temp, idx, st);
-        if (per <= 2) return launch_resident<2>(b, n, m, L, xyz, temp, idx, st);
-        if (per <= 4) return launch_resident<4>(b, n, m, L, xyz, temp, idx, st);
-        if (per <= 8) return launch_resident<8>(b, n, m, L, xyz, temp, idx, st);
-        return launch_resident<16>(b, n, m, L, xyz, temp, idx, st);
+        const int q = (n + (1 << L) - 1) >> L;  // points per reference thread
+        int qbits = 0;
+        while ((1 << qbits) < q) ++qbits;
+        if (n <= 256) return launch_bucket<1, 1>(b, n, m, L, qbits, xyz, temp, idx, st);    //   8 buckets of  32
+        if (n <= 1024) return launch_bucket<4, 1>(b, n, m, L, qbits, xyz, temp, idx, st);   //  32 buckets of  32
+        if (n <= 4096) return launch_bucket<16, 1>(b, n, m, L, qbits, xyz, temp, idx, st);  // 128 buckets of  32
+        return launch_bucket<16, 4>(b, n, m, L, qbits, xyz, temp, idx, st);                 // 128 buckets of 128
     }
     fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx);
     EPNET_RETURN_LAUNCH_STATUS();
