@@ -178,7 +178,7 @@ def main():
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_pool[:4]]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
 
-    use_graph = args.impl == "ours" and not args.no_graph and hasattr(model, "make_runner")
+    use_graph = args.impl == "ours" and not args.no_graph
     runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device) if use_graph else None
 
     out_host = None

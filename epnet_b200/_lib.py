@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-_c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+_c_int, _c_float, _c_void_p, _c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 
 # name -> argtypes, exactly the declarations of include/epnet_b200.h
 SIGNATURES = {
@@ -22,6 +22,11 @@ SIGNATURES = {
     "epnet_three_interpolate_grad": [_c_int] * 4 + [_c_void_p] * 5,
     "epnet_grid_gather_bilinear": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
     "epnet_grid_gather_bilinear_grad": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
+    "epnet_fps_sample": [_c_int] * 3 + [_c_void_p] * 6 + [_c_int, _c_void_p],
+    "epnet_group_concat": [_c_int] * 5 + [_c_void_p] * 6,
+    "epnet_bias_relu": [_c_int, _c_int, _c_ll, _c_void_p, _c_void_p, _c_void_p],
+    "epnet_bias_relu_maxpool": [_c_int] * 4 + [_c_void_p] * 3 + [_c_ll, _c_void_p],
+    "epnet_three_interpolate_concat": [_c_int] * 5 + [_c_void_p] * 6,
 }
 
 

@@ -79,7 +79,8 @@ __device__ __forceinline__ void warp_argmax(uint32_t &bits, uint32_t &tie)
 // order, i.e. the ones a new sample touches together, are updated by different warps in parallel.
 template <int NW, int kSlots>
 __global__ void __launch_bounds__(NW * 32, 1)
-fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx)
+fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
+                  float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
 {
     constexpr int T = NW * 32;
     constexpr int CAP = T * kBuckets * kSlots;  // sorted positions this CTA can hold
@@ -108,11 +109,26 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     xyz += (size_t)scene * n * 3;
     temp += (size_t)scene * n;
     idx += (size_t)scene * m;
+    if (new_xyz) new_xyz += (size_t)scene * m * 3;
+    if (aux_out) {
+        aux_in += (size_t)scene * n * aux_dim;
+        aux_out += (size_t)scene * m * aux_dim;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inf = __int_as_float(0x7f800000);
 
-    if (tid == 0) idx[0] = 0;
-    if (m == 1) return;
+    if (tid == 0) {
+        idx[0] = 0;
+        if (new_xyz) {
+            new_xyz[0] = __ldg(xyz);
+            new_xyz[1] = __ldg(xyz + 1);
+            new_xyz[2] = __ldg(xyz + 2);
+        }
+    }
+    if (m == 1) {
+        if (aux_out && tid < aux_dim) aux_out[tid] = __ldg(aux_in + tid);
+        return;
+    }
 
     // ---------------- 1. scene bounding box ----------------
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
@@ -357,7 +373,23 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
         cx = xs[pos];
         cy = ys[pos];
         cz = zs[pos];
-        if (tid == 0) idx[j] = (int)fps_key_to_index(wkey >> 16, L, qbits);
+        if (tid == 0) {
+            idx[j] = (int)fps_key_to_index(wkey >> 16, L, qbits);
+            if (new_xyz) {
+                new_xyz[3 * j] = cx;
+                new_xyz[3 * j + 1] = cy;
+                new_xyz[3 * j + 2] = cz;
+            }
+        }
+    }
+
+    // per-sample payload (LI-Fusion pixel coordinates) follows the samples: aux_out[j] = aux_in[idx[j]]
+    if (aux_out) {
+        __syncthreads();  // idx[] written by thread 0 is visible to the CTA
+        for (int e = tid; e < m * aux_dim; e += T) {
+            const int j = e / aux_dim, a = e - j * aux_dim;
+            aux_out[e] = __ldg(aux_in + (size_t)idx[j] * aux_dim + a);
+        }
     }
 
     // temp is an in/out buffer in the reference: leave the final running distances behind
@@ -377,7 +409,8 @@ __device__ __forceinline__ uint32_t fps_tie_decode(uint32_t tie, int L)
 }
 
 __global__ void __launch_bounds__(1024, 1)
-fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx)
+fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
+                     float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
 {
     __shared__ FpsCand slots[2][32];
     const int scene = blockIdx.x;
@@ -386,6 +419,11 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
     idx += (size_t)scene * m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int L = 10;
+    if (new_xyz) new_xyz += (size_t)scene * m * 3;
+    if (aux_out) {
+        aux_in += (size_t)scene * n * aux_dim;
+        aux_out += (size_t)scene * m * aux_dim;
+    }
     if (tid == 0) idx[0] = 0;
 
     uint32_t last = 0;
@@ -416,24 +454,30 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
         last = fps_tie_decode(tie, L);
         if (tid == 0) idx[j] = (int)last;
     }
+    __syncthreads();
+    for (int e = tid; e < m * 3 && new_xyz; e += 1024) new_xyz[e] = __ldg(xyz + 3 * idx[e / 3] + e % 3);
+    for (int e = tid; e < m * aux_dim && aux_out; e += 1024) aux_out[e] = __ldg(aux_in + (size_t)idx[e / aux_dim] * aux_dim + e % aux_dim);
 }
 
 template <int NW, int kSlots>
-static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, cudaStream_t st)
+static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
+                         const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
 {
     const size_t smem = (size_t)3 * NW * 32 * kBuckets * kSlots * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<NW, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    fps_bucket_kernel<NW, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx);
+    fps_bucket_kernel<NW, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
 }  // namespace epnet
 
-EPNET_API int epnet_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream)
+static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
+                        float *aux_out, int aux_dim, void *stream)
 {
     using namespace epnet;
     if (b < 0 || n <= 0 || m < 0 || !xyz || !temp || !idx) return EPNET_ERR_BAD_ARG;
+    if ((aux_out != nullptr) != (aux_in != nullptr) || (aux_out && (aux_dim < 1 || aux_dim > 4))) return EPNET_ERR_BAD_ARG;
     if (b == 0 || m == 0) return EPNET_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int L = 0;
@@ -442,11 +486,24 @@ EPNET_API int epnet_furthest_point_sampling(int b, int n, int m, const float *xy
         const int q = (n + (1 << L) - 1) >> L;  // points per reference thread
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
-        if (n <= 256) return launch_bucket<1, 1>(b, n, m, L, qbits, xyz, temp, idx, st);    //   8 buckets of  32
-        if (n <= 1024) return launch_bucket<4, 1>(b, n, m, L, qbits, xyz, temp, idx, st);   //  32 buckets of  32
-        if (n <= 4096) return launch_bucket<16, 1>(b, n, m, L, qbits, xyz, temp, idx, st);  // 128 buckets of  32
-        return launch_bucket<16, 4>(b, n, m, L, qbits, xyz, temp, idx, st);                 // 128 buckets of 128
+#define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st
+        if (n <= 256) return launch_bucket<1, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32
+        if (n <= 1024) return launch_bucket<4, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
+        if (n <= 4096) return launch_bucket<16, 1>(EPNET_FPS_ARGS);  // 128 buckets of  32
+        return launch_bucket<16, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
+#undef EPNET_FPS_ARGS
     }
-    fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx);
+    fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
     EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream)
+{
+    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, nullptr, nullptr, 0, stream);
+}
+
+EPNET_API int epnet_fps_sample(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
+                               float *aux_out, int aux_dim, void *stream)
+{
+    return fps_dispatch(b, n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, stream);
 }

@@ -122,3 +122,38 @@ def grid_gather_bilinear_grad_wrapper(b, c, h, w, n, grad_out_tensor, xy_tensor,
     _call("grid_gather_bilinear_grad", LIB.epnet_grid_gather_bilinear_grad, grad_out_tensor, b, c, h, w, n,
           _f(grad_out_tensor, "grad_out"), _f(xy_tensor, "xy"), int(bool(align_corners)),
           _f(grad_fmap_tensor, "grad_feature_map"))
+
+
+# ---- fused entry points (include/epnet_b200.h); used by epnet_b200.runner, not by the reference surface ----
+
+def _opt(t, dtype, name):
+    return None if t is None else _dev_ptr(t, dtype, name)
+
+
+def fps_sample_wrapper(b, n, m, xyz, temp, idx, new_xyz=None, aux_in=None, aux_out=None):
+    aux_dim = 0 if aux_in is None else aux_in.shape[-1]
+    _call("fps_sample", LIB.epnet_fps_sample, xyz, b, n, m, _f(xyz, "xyz"), _f(temp, "temp"), _i(idx, "idx"),
+          _opt(new_xyz, torch.float32, "new_xyz"), _opt(aux_in, torch.float32, "aux_in"),
+          _opt(aux_out, torch.float32, "aux_out"), aux_dim)
+
+
+def group_concat_wrapper(b, c, n, m, nsample, xyz, new_xyz, features, idx, out):
+    _call("group_concat", LIB.epnet_group_concat, xyz, b, c, n, m, nsample, _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
+          _opt(features, torch.float32, "features"), _i(idx, "idx"), _f(out, "out"))
+
+
+def bias_relu_wrapper(b, c, l, x, bias):
+    _call("bias_relu", LIB.epnet_bias_relu, x, b, c, l, _f(x, "x"), _f(bias, "bias"))
+
+
+def bias_relu_maxpool_wrapper(b, c, m, nsample, x, bias, out_ptr, out_batch_stride):
+    """out_ptr: raw device address of out[0, c_offset, 0] inside a (B, C_total, M) buffer with batch stride
+    out_batch_stride floats."""
+    _call("bias_relu_maxpool", LIB.epnet_bias_relu_maxpool, x, b, c, m, nsample, _f(x, "x"), _f(bias, "bias"), out_ptr,
+          out_batch_stride)
+
+
+def three_interpolate_concat_wrapper(b, c2, m, n, c1, known_feats, idx, dist2, skip_feats, out):
+    _call("three_interpolate_concat", LIB.epnet_three_interpolate_concat, known_feats, b, c2, m, n, c1,
+          _f(known_feats, "known_feats"), _i(idx, "idx"), _f(dist2, "dist2"), _opt(skip_feats, torch.float32, "skip_feats"),
+          _f(out, "out"))

@@ -1,0 +1,265 @@
+"""Inference runner for the RPN backbone: the same network as Pointnet2MSG.forward (the mirror of
+/root/reference/lib/net/pointnet2_msg.py:201-248), scheduled B200-first.
+
+What changes relative to the op-by-op module path (nothing changes in WHAT is computed):
+  * three streams inside ONE captured CUDA graph: the furthest-point-sampling chain of all four levels (it
+    depends on coordinates only), the image stream (cuDNN convolutions), and the point stream; the ~300 tiny
+    launches of a forward become one graph replay with parallel branches;
+  * eval-mode BatchNorm is folded into the preceding convolution / 1x1 conv (w' = w*g/sqrt(v+eps),
+    b' = beta - mean*g/sqrt(v+eps));
+  * fused kernels from libepnet_b200.so: FPS emits new_xyz and the gathered pixel coordinates itself;
+    ball-query indices feed one group+recentre+concat launch that writes the GEMM operand; the last MLP
+    layer's bias+ReLU is fused with the max-pool and writes into the multi-scale concat; three_nn distances
+    feed one weights+interpolate+concat launch;
+  * shared 1x1 convolutions run as batched GEMMs (cuBLAS, strict fp32) on (B, C, L) operands.
+Only eval mode is supported here (train mode needs batch statistics: use the module path).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import pointnet2_cuda as pc
+
+
+def _fold_bn(weight2d, conv_bias, bn):
+    """conv(1x1) [+bias] followed by eval-mode BatchNorm -> (W', b')."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = weight2d * scale[:, None]
+    b = bn.bias - bn.running_mean * scale
+    if conv_bias is not None:
+        b = b + conv_bias * scale
+    return w.contiguous(), b.contiguous()
+
+
+def _fold_shared_mlp(mlp):
+    layers = []
+    for unit in mlp:  # layer0, layer1, ...: Sequential(conv, bn(bn), activation)
+        conv = unit.conv
+        w2d = conv.weight.reshape(conv.out_channels, conv.in_channels)
+        if hasattr(unit, "bn"):
+            layers.append(_fold_bn(w2d, conv.bias, unit.bn.bn))
+        else:
+            bias = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=w2d.device)
+            layers.append((w2d.contiguous(), bias.contiguous()))
+    return layers
+
+
+class _Fusion:
+    """Folded parameters of Atten_Fusion_Conv / Fusion_Conv (lib/net/pointnet2_msg.py:35-104)."""
+
+    def __init__(self, mod):
+        self.attention = hasattr(mod, "IA_Layer")
+        if self.attention:
+            ia = mod.IA_Layer
+            self.w1, self.b1 = ia.fc1.weight.contiguous(), ia.fc1.bias
+            self.w2, self.b2 = ia.fc2.weight.contiguous(), ia.fc2.bias
+            self.w3, self.b3 = ia.fc3.weight.contiguous(), ia.fc3.bias
+            conv, bn = ia.conv1[0], ia.conv1[1]
+            self.wc, self.bc = _fold_bn(conv.weight.squeeze(-1), conv.bias, bn)
+        w, b = _fold_bn(mod.conv1.weight.squeeze(-1), mod.conv1.bias, mod.bn1)
+        self.wf, self.bf = w, b
+
+    def __call__(self, point, img):
+        """point (B,Cp,M), img (B,Ci,M) -> (B,Cp,M)"""
+        B, _, M = point.shape
+        if self.attention:
+            r = torch.matmul(self.w1, img) + torch.matmul(self.w2, point) + (self.b1 + self.b2)[:, None]
+            att = torch.sigmoid(torch.matmul(self.w3, torch.tanh(r)) + self.b3[:, None])  # (B,1,M)
+            img_new = torch.matmul(self.wc, img)
+            pc.bias_relu_wrapper(B, img_new.shape[1], M, img_new, self.bc)
+            img = img_new * att
+        out = torch.matmul(self.wf, torch.cat([point, img], dim=1))
+        pc.bias_relu_wrapper(B, out.shape[1], M, out, self.bf)
+        return out
+
+
+class BackboneRunner:
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True):
+        if model.training:
+            raise RuntimeError("BackboneRunner folds BatchNorm: call model.eval() first (train mode: use model(...) itself)")
+        c = model.config
+        if c.input_channels != 0:
+            raise NotImplementedError("runner covers the published config (xyz-only input, RPN.USE_INTENSITY False)")
+        self.model, self.cfg, self.device = model, c, device
+        self.B, self.N = batch, npoints
+        H, W = image_hw
+        f32 = dict(dtype=torch.float32, device=device)
+        self.points = torch.zeros(batch, npoints, 3, **f32)
+        self.image = torch.zeros(batch, 3, H, W, **f32)
+        self.xy = torch.zeros(batch, npoints, 2, **f32)
+        self._xy_scale = torch.tensor([c.image_size[0] - 1.0, c.image_size[1] - 1.0], **f32)
+
+        with torch.no_grad():
+            self.sa = []
+            for k, sa in enumerate(model.SA_modules):
+                scales = []
+                for grouper, mlp in zip(sa.groupers, sa.mlps):
+                    scales.append((float(grouper.radius), int(grouper.nsample), _fold_shared_mlp(mlp)))
+                self.sa.append((int(sa.npoint), scales))
+            self.fp = [_fold_shared_mlp(fp.mlp) for fp in model.FP_modules]
+            if c.li_fusion:
+                self.img_blocks = []
+                for blk in model.Img_Block:
+                    w1, b1 = _fold_bn(blk.conv1.weight.flatten(1), None, blk.bn1)
+                    self.img_blocks.append((w1.view_as(blk.conv1.weight).contiguous(), b1, blk.conv1.stride, blk.conv2))
+                self.fusion = [_Fusion(m) for m in model.Fusion_Conv]
+                self.final_fusion = _Fusion(model.final_fusion_img_point)
+                wq, bq = _fold_bn(model.image_fusion_conv.weight.flatten(1), model.image_fusion_conv.bias, model.image_fusion_bn)
+                self.img_fuse_w, self.img_fuse_b = wq.view_as(model.image_fusion_conv.weight).contiguous(), bq
+
+        self.s_fps = torch.cuda.Stream(device=device)
+        self.s_img = torch.cuda.Stream(device=device)
+        self.kernel_launches_per_replay = 0
+        self.graph = None
+        self.out = None
+        if use_graph:
+            self._capture()
+
+    # ------------------------------------------------------------------------------------ pieces
+    def _mlp_pool(self, x, layers, B, M, ns, out_buf, c_off):
+        """x (B,Cin,M*ns) -> max over ns of the shared MLP, written into out_buf[:, c_off:c_off+Cout, :]."""
+        L = M * ns
+        for li, (w, b) in enumerate(layers):
+            x = torch.matmul(w, x)  # (B,Cout,L) batched GEMM, strict fp32
+            if li + 1 < len(layers):
+                pc.bias_relu_wrapper(B, w.shape[0], L, x, b)
+        cout = layers[-1][0].shape[0]
+        pc.bias_relu_maxpool_wrapper(B, cout, M, ns, x, layers[-1][1], out_buf.data_ptr() + 4 * c_off * M,
+                                     out_buf.shape[1] * M)
+        return cout
+
+    def _mlp(self, x, layers, B, L):
+        for w, b in layers:
+            x = torch.matmul(w, x)
+            pc.bias_relu_wrapper(B, w.shape[0], L, x, b)
+        return x
+
+    def _forward(self):
+        c, B, N, dev = self.cfg, self.B, self.N, self.device
+        main = torch.cuda.current_stream(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        xyz0 = self.points
+        xyn = self.xy / self._xy_scale * 2.0 - 1.0 if c.li_fusion else None  # pointnet2_msg.py:208-210
+
+        # ---- FPS chain of all levels (coordinates only) on its own stream ----
+        ready = torch.cuda.Event()
+        ready.record(main)
+        l_xyz, l_xy, fps_done = [xyz0], [xyn], []
+        with torch.cuda.stream(self.s_fps):
+            self.s_fps.wait_event(ready)
+            cur_xyz, cur_xy = xyz0, xyn
+            for npoint, _ in self.sa:
+                n = cur_xyz.shape[1]
+                temp = torch.full((B, n), 1e10, **f32)
+                idx = torch.empty((B, npoint), dtype=torch.int32, device=dev)
+                new_xyz = torch.empty((B, npoint, 3), **f32)
+                new_xy = torch.empty((B, npoint, 2), **f32) if c.li_fusion else None
+                pc.fps_sample_wrapper(B, n, npoint, cur_xyz, temp, idx, new_xyz, cur_xy, new_xy)
+                ev = torch.cuda.Event()
+                ev.record(self.s_fps)
+                fps_done.append(ev)
+                l_xyz.append(new_xyz)
+                l_xy.append(new_xy)
+                cur_xyz, cur_xy = new_xyz, new_xy
+
+        # ---- image stream ----
+        imgs, img_done, img_fusion, img_fusion_done = [], [], None, None
+        if c.li_fusion:
+            with torch.cuda.stream(self.s_img):
+                self.s_img.wait_event(ready)
+                x = self.image
+                for (w1, b1, stride, conv2) in self.img_blocks:
+                    x = F.conv2d(x, w1, b1, stride=stride, padding=1)
+                    x = conv2(F.relu_(x))
+                    ev = torch.cuda.Event()
+                    ev.record(self.s_img)
+                    imgs.append(x)
+                    img_done.append(ev)
+                de = torch.cat([self.model.DeConv[i](imgs[i]) for i in range(len(imgs))], dim=1)
+                img_fusion = F.relu_(F.conv2d(de, self.img_fuse_w, self.img_fuse_b))
+                img_fusion_done = torch.cuda.Event()
+                img_fusion_done.record(self.s_img)
+
+        # ---- point stream ----
+        l_feat = [None]
+        for k, (npoint, scales) in enumerate(self.sa):
+            main.wait_event(fps_done[k])
+            xyz, new_xyz, feats = l_xyz[k], l_xyz[k + 1], l_feat[k]
+            n = xyz.shape[1]
+            cin = 0 if feats is None else feats.shape[1]
+            ctot = sum(layers[-1][0].shape[0] for _, _, layers in scales)
+            out = torch.empty((B, ctot, npoint), **f32)
+            c_off = 0
+            for radius, ns, layers in scales:
+                bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
+                pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
+                grouped = torch.empty((B, 3 + cin, npoint * ns), **f32)
+                pc.group_concat_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, feats, bidx, grouped)
+                c_off += self._mlp_pool(grouped, layers, B, npoint, ns, out, c_off)
+            if c.li_fusion:
+                main.wait_event(img_done[k])
+                img = imgs[k]
+                gathered = torch.empty((B, img.shape[1], npoint), **f32)
+                pc.grid_gather_bilinear_wrapper(B, img.shape[1], img.shape[2], img.shape[3], npoint, img, l_xy[k + 1],
+                                                c.align_corners, gathered)
+                out = self.fusion[k](out, gathered)
+            l_feat.append(out)
+
+        for i in range(-1, -(len(self.fp) + 1), -1):
+            unknown, known = l_xyz[i - 1], l_xyz[i]
+            n, m = unknown.shape[1], known.shape[1]
+            skip, kf = l_feat[i - 1], l_feat[i]
+            c1 = 0 if skip is None else skip.shape[1]
+            dist2 = torch.empty((B, n, 3), **f32)
+            idx3 = torch.empty((B, n, 3), dtype=torch.int32, device=dev)
+            pc.three_nn_wrapper(B, n, m, unknown, known, dist2, idx3)
+            cat = torch.empty((B, kf.shape[1] + c1, n), **f32)
+            pc.three_interpolate_concat_wrapper(B, kf.shape[1], m, n, c1, kf, idx3, dist2, skip, cat)
+            l_feat[i - 1] = self._mlp(cat, self.fp[i], B, n)
+
+        feats = l_feat[0]
+        if c.li_fusion:
+            main.wait_event(img_fusion_done)
+            g = torch.empty((B, img_fusion.shape[1], N), **f32)
+            pc.grid_gather_bilinear_wrapper(B, img_fusion.shape[1], img_fusion.shape[2], img_fusion.shape[3], N, img_fusion, xyn,
+                                            c.align_corners, g)
+            feats = self.final_fusion(feats, g)
+        main.wait_stream(self.s_fps)
+        main.wait_stream(self.s_img)
+        return xyz0, feats
+
+    # ------------------------------------------------------------------------------------ graph
+    def _capture(self):
+        dev = self.device
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm), torch.no_grad():
+            for _ in range(3):  # cuDNN/cuBLAS autotuning and workspace allocation happen outside capture
+                self._forward()
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        before = pc.LAUNCHES[0]
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self._forward()
+        self.kernel_launches_per_replay = pc.LAUNCHES[0] - before
+
+    def _load(self, points, image, xy):
+        self.points.copy_(points, non_blocking=True)
+        self.image.copy_(image, non_blocking=True)
+        self.xy.copy_(xy, non_blocking=True)
+
+    def __call__(self, points, image, xy):
+        """points (B,N,3), image (B,3,H,W), xy (B,N,2) pixel coordinates (host-pinned or device; NOT modified) ->
+        (xyz (B,N,3), features (B,128,N)) in buffers owned by the runner, valid until the next call."""
+        self._load(points, image, xy)
+        if self.graph is None:
+            with torch.no_grad():
+                return self._forward()
+        self.graph.replay()
+        return self.out
+
+    def eager(self, points, image, xy):
+        """Same schedule without the graph (profiling: events around individual launches)."""
+        self._load(points, image, xy)
+        with torch.no_grad():
+            return self._forward()

@@ -70,6 +70,41 @@ int epnet_grid_gather_bilinear(int b, int c, int h, int w, int n, const float *f
 /* gradient w.r.t. fmap; grad_fmap (B,C,H,W) arrives zeroed */
 int epnet_grid_gather_bilinear_grad(int b, int c, int h, int w, int n, const float *grad_out, const float *xy, int align_corners, float *grad_fmap, void *stream);
 
+/* ---- fused entry points (no reference launcher has these signatures; each names the reference
+ *      Python lines whose op-by-op composition it replaces) ----------------------------------- */
+
+/* furthest point sampling that also emits what the set-abstraction level needs next, replacing
+ * FPS + transpose + gather_operation + transpose (pointnet2_modules.py:41-45) and, for LI-Fusion, the
+ * index widening + torch.gather of the pixel coordinates (lib/net/pointnet2_msg.py:218-219):
+ *   idx (B,M); new_xyz (B,M,3) = xyz[idx] (may be NULL); aux_out (B,M,aux_dim) = aux_in (B,N,aux_dim)[idx]
+ *   (aux_in/aux_out may be NULL, aux_dim <= 4).  Same sampling, same temp contract as
+ *   epnet_furthest_point_sampling. */
+int epnet_fps_sample(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
+                     float *aux_out, int aux_dim, void *stream);
+
+/* QueryAndGroup.forward minus the ball query (pointnet2_utils.py:250-257) in one launch:
+ *   out (B,3+C,M,ns): rows 0..2 = xyz[idx] - new_xyz (re-centred coordinates), rows 3.. = features[:, idx].
+ * xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL with c = 0, idx (B,M,ns). */
+int epnet_group_concat(int b, int c, int n, int m, int nsample, const float *xyz, const float *new_xyz, const float *features,
+                       const int *idx, float *out, void *stream);
+
+/* in place x[b,c,:] = max(x[b,c,:] + bias[c], 0) over x (B,C,L): the BatchNorm(eval)+ReLU tail of a
+ * SharedMLP layer (pytorch_utils.py:20-32) once BN is folded into the 1x1 convolution. */
+int epnet_bias_relu(int b, int c, long long l, float *x, const float *bias, void *stream);
+
+/* out[b,c,p] = max_s max(x[b,c,p,s] + bias[c], 0): last SharedMLP layer's tail fused with
+ * F.max_pool2d(kernel=[1,nsample]) + squeeze (pointnet2_modules.py:59-68).  x (B,C,M,ns) -> out with
+ * batch stride out_batch_stride floats (so it can write straight into the MSG concat, :72). */
+int epnet_bias_relu_maxpool(int b, int c, int m, int nsample, const float *x, const float *bias, float *out,
+                            long long out_batch_stride, void *stream);
+
+/* PointnetFPModule.forward between three_nn and the MLP (pointnet2_modules.py:157-166) in one launch:
+ * inverse-distance weights from the SQUARED distances (sqrt, 1/(d+1e-8), normalise), three_interpolate of
+ * known_feats (B,C2,m), and the concat with the skip features (B,C1,n) (NULL with c1 = 0):
+ *   out (B,C2+C1,n). */
+int epnet_three_interpolate_concat(int b, int c2, int m, int n, int c1, const float *known_feats, const int *idx,
+                                   const float *dist2, const float *skip_feats, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,88 @@
+"""Whole-backbone parity on the GPU (strict fp32: TF32 off on both sides):
+  1. the module path on the B200 kernels == the same modules on the reference's own kernels + ATen grid_sample;
+  2. the graph runner (folded BN, fused kernels, three streams) == the module path, to float tolerance, with
+     identical sampled indices (any FPS / ball-query difference would change the output completely)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _models(n_extra_eval_noise=True):
+    from epnet_b200 import BackboneConfig, Pointnet2MSG
+    torch.manual_seed(0)
+    ours = Pointnet2MSG(config=BackboneConfig()).cuda().eval()
+    # non-trivial BatchNorm statistics so that folding is actually exercised
+    g = torch.Generator().manual_seed(1)
+    for mod in ours.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    return ours
+
+
+def _close(a, b, rel):
+    scale = b.abs().max().item()
+    err = (a - b).abs().max().item()
+    assert err <= rel * scale, "max abs err %.3e vs scale %.3e (rel %.2e > %.1e)" % (err, scale, err / scale, rel)
+
+
+def test_module_path_equals_reference_kernels():
+    from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
+    from epnet_b200.pointnet2_utils import make_ops
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    _strict_fp32()
+    ours = _models()
+
+    def aten_gather(fm, xy):
+        return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
+
+    ref = Pointnet2MSG(config=BackboneConfig(), ops=make_ops(ref_cuda), feature_gather=aten_gather, reference_composition=True).cuda().eval()
+    ref.load_state_dict(ours.state_dict())
+    data = {k: v.cuda() for k, v in scenes.batch(1000, 2, 16384).items()}
+    with torch.no_grad():
+        xyz_o, f_o = ours(data["points"], data["image"], data["xy"].clone())
+        xyz_r, f_r = ref(data["points"], data["image"], data["xy"].clone())
+    assert torch.equal(xyz_o, xyz_r)
+    # same indices, same cuDNN convs; only the bilinear gather differs in rounding -> 1e-5 of the output scale
+    _close(f_o, f_r, 1e-5)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_runner_equals_module_path(use_graph):
+    from epnet_b200 import scenes
+    _strict_fp32()
+    ours = _models()
+    runner = ours.make_runner(2, 16384, torch.device("cuda"), use_graph=use_graph)
+    for seed in (1000, 1020):
+        data = {k: v.cuda() for k, v in scenes.batch(seed, 2, 16384).items()}
+        with torch.no_grad():
+            xyz_m, f_m = ours(data["points"], data["image"], data["xy"].clone())
+        xy_before = data["xy"].clone()
+        xyz_r, f_r = runner(data["points"], data["image"], data["xy"])
+        torch.cuda.synchronize()
+        assert torch.equal(data["xy"], xy_before)  # the runner does not touch the caller's xy
+        assert torch.equal(xyz_r, xyz_m)
+        assert f_r.shape == f_m.shape == (2, 128, 16384)
+        # BN folding and GEMM re-association move results by a few fp32 ulps per layer
+        _close(f_r, f_m, 2e-5)
+
+
+def test_state_dict_keys_match_reference_naming():
+    from epnet_b200 import Pointnet2MSG
+    keys = set(Pointnet2MSG().state_dict().keys())
+    for k in ("SA_modules.0.mlps.0.layer0.conv.weight", "SA_modules.0.mlps.0.layer0.bn.bn.running_mean",
+              "FP_modules.3.mlp.layer1.bn.bn.weight", "Img_Block.0.conv1.weight", "Fusion_Conv.0.IA_Layer.fc1.weight",
+              "Fusion_Conv.0.IA_Layer.conv1.0.weight", "DeConv.3.weight", "image_fusion_conv.bias",
+              "final_fusion_img_point.bn1.running_var"):
+        assert k in keys, k
