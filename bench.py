@@ -221,10 +221,8 @@ def main():
     ms_e2e = timed_region(step_e2e, args.steps, rank_sync)
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host)
 
-    if distributed:
-        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+    from epnet_b200 import shard
+    ms, ms_e2e = shard.max_over_ranks([ms, ms_e2e], device)  # slowest rank defines the job's time
 
     scenes_total = BATCH_PER_GPU * world * args.steps
     line = {
