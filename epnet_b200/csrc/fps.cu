@@ -24,12 +24,12 @@
 // tie words in registers (lane l of warp w owns sorted positions (((b*NW+w)*kSlots+i)*32+l), bucket boxes and
 // cached winners in the registers of lanes 0..7.  One __syncthreads per iteration (none when a single
 // warp holds the whole cloud, N <= 1024).  N > 16384 streams from L2 (fps_streaming_kernel).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace epnet {
 
 constexpr int kFpsMaxResident = 16384;  // 3 planes * 4 B * 16384 = 192 KB of the 227 KB shared memory
-constexpr int kBuckets = 8;             // buckets per warp
 constexpr float kBoxDeflate = 0.999996f;  // > (1 - 2^-18): covers the few-ulp rounding of both distance evaluations
 
 struct FpsCand {
@@ -74,10 +74,10 @@ __device__ __forceinline__ void warp_argmax(uint32_t &bits, uint32_t &tie)
     bits = mx;
 }
 
-// NW warps, kBuckets buckets per warp, kSlots points per lane per bucket (bucket = 32*kSlots sorted points).
+// NW warps, kBuckets buckets per warp (lane b keeps bucket b's box), kSlots points per lane per bucket (bucket = 32*kSlots sorted points).
 // Buckets are dealt to warps round-robin (bucket g -> warp g % NW): buckets that are neighbours in Morton
 // order, i.e. the ones a new sample touches together, are updated by different warps in parallel.
-template <int NW, int kSlots>
+template <int NW, int kBuckets, int kSlots>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
                   float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
@@ -86,8 +86,9 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     constexpr int CAP = T * kBuckets * kSlots;  // sorted positions this CTA can hold
     constexpr int PPT = CAP / T;                // points per thread during the sort
     constexpr int NCELL = CAP;                  // one cell per sorted position on average; the histogram aliases one plane
-    constexpr int CB = NW == 1 ? (kSlots == 1 ? 8 : 10) : NW == 4 ? (kSlots == 1 ? 10 : 12) : (kSlots == 1 ? 12 : 14);
+    constexpr int CB = CAP == 256 ? 8 : CAP == 1024 ? 10 : CAP == 4096 ? 12 : 14;
     static_assert((1 << CB) == NCELL, "cell bits");
+    static_assert(kBuckets <= 32, "one lane per bucket");
 #define FPS_POS(b, i) ((((b) * NW + warp) * kSlots + (i)) * 32 + lane)
 
     extern __shared__ __align__(16) float fps_smem[];
@@ -323,6 +324,8 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
 
     // ---------------- 7. the sampling loop ----------------
     float cx = __ldg(xyz), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // sample 0 is point 0
+    uint32_t warp_bits = lane < kBuckets ? bmax : 0u, warp_key = lane < kBuckets ? bkey : 0xffffffffu;
+    warp_argmax(warp_bits, warp_key);
     for (int j = 1; j < m; ++j) {
         // which buckets can change?  box distance (deflated) vs the bucket's largest running distance
         const float ex = fmaxf(fmaxf(blo_x - cx, cx - bhi_x), 0.f);
@@ -354,19 +357,22 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
                 }
             }
         }
-        // winner of the warp's 8 buckets, then of the CTA
-        uint32_t wbits = lane < kBuckets ? bmax : 0u;
-        uint32_t wkey = lane < kBuckets ? bkey : 0xffffffffu;
-        warp_argmax(wbits, wkey);
+        // winner of the warp's buckets (unchanged if none of them was touched), then of the CTA
+        if (mask) {
+            warp_bits = lane < kBuckets ? bmax : 0u;
+            warp_key = lane < kBuckets ? bkey : 0xffffffffu;
+            warp_argmax(warp_bits, warp_key);
+        }
+        uint32_t wbits = warp_bits, wkey = warp_key;
         if (NW > 1) {
-            FpsCand *s = slots[j & 1];
+            const int par = j & 1;
             if (lane == 0) {
-                s[warp].dist_bits = wbits;
-                s[warp].tie = wkey;
+                slots[par][warp].dist_bits = wbits;
+                slots[par][warp].tie = wkey;
             }
             __syncthreads();
-            wbits = lane < NW ? s[lane].dist_bits : 0u;
-            wkey = lane < NW ? s[lane].tie : 0xffffffffu;
+            wbits = lane < NW ? slots[par][lane].dist_bits : 0u;
+            wkey = lane < NW ? slots[par][lane].tie : 0xffffffffu;
             warp_argmax(wbits, wkey);
         }
         const uint32_t pos = wkey & 0xffffu;
@@ -459,14 +465,14 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
     for (int e = tid; e < m * aux_dim && aux_out; e += 1024) aux_out[e] = __ldg(aux_in + (size_t)idx[e / aux_dim] * aux_dim + e % aux_dim);
 }
 
-template <int NW, int kSlots>
+template <int NW, int kBuckets, int kSlots>
 static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
 {
     const size_t smem = (size_t)3 * NW * 32 * kBuckets * kSlots * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<NW, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<NW, kBuckets, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    fps_bucket_kernel<NW, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
+    fps_bucket_kernel<NW, kBuckets, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
@@ -487,10 +493,16 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
 #define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st
-        if (n <= 256) return launch_bucket<1, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32
-        if (n <= 1024) return launch_bucket<4, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
-        if (n <= 4096) return launch_bucket<16, 1>(EPNET_FPS_ARGS);  // 128 buckets of  32
-        return launch_bucket<16, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
+        static const int variant = getenv("EPNET_FPS_VARIANT") ? atoi(getenv("EPNET_FPS_VARIANT")) : 0;  // tuning knob
+        if (n <= 256) return launch_bucket<1, 8, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32
+        if (n <= 1024) return launch_bucket<4, 8, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
+        if (n <= 4096) {
+            if (variant == 1) return launch_bucket<8, 16, 1>(EPNET_FPS_ARGS);  // 128 buckets of 32, 8 warps
+            if (variant == 2) return launch_bucket<4, 8, 4>(EPNET_FPS_ARGS);   //  32 buckets of 128, 4 warps
+            return launch_bucket<16, 8, 1>(EPNET_FPS_ARGS);                    // 128 buckets of 32
+        }
+        if (variant == 1) return launch_bucket<8, 16, 4>(EPNET_FPS_ARGS);      // 128 buckets of 128, 8 warps
+        return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                        // 128 buckets of 128
 #undef EPNET_FPS_ARGS
     }
     fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);

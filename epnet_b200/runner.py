@@ -168,14 +168,16 @@ class BackboneRunner:
                 self.s_img.wait_event(ready)
                 x = self.image
                 for (w1, b1, stride, conv2) in self.img_blocks:
-                    x = F.conv2d(x, w1, b1, stride=stride, padding=1)
-                    x = conv2(F.relu_(x))
+                    x = F.conv2d(x, w1, None, stride=stride, padding=1)
+                    pc.bias_relu_wrapper(B, x.shape[1], x.shape[2] * x.shape[3], x, b1)  # folded BN bias + ReLU, one pass
+                    x = conv2(x)
                     ev = torch.cuda.Event()
                     ev.record(self.s_img)
                     imgs.append(x)
                     img_done.append(ev)
                 de = torch.cat([self.model.DeConv[i](imgs[i]) for i in range(len(imgs))], dim=1)
-                img_fusion = F.relu_(F.conv2d(de, self.img_fuse_w, self.img_fuse_b))
+                img_fusion = F.conv2d(de, self.img_fuse_w, None)
+                pc.bias_relu_wrapper(B, img_fusion.shape[1], img_fusion.shape[2] * img_fusion.shape[3], img_fusion, self.img_fuse_b)
                 img_fusion_done = torch.cuda.Event()
                 img_fusion_done.record(self.s_img)
 
