@@ -27,6 +27,7 @@ SIGNATURES = {
     "epnet_bias_relu": [_c_int, _c_int, _c_ll, _c_void_p, _c_void_p, _c_void_p],
     "epnet_bias_relu_maxpool": [_c_int] * 4 + [_c_void_p] * 3 + [_c_ll, _c_void_p],
     "epnet_three_interpolate_concat": [_c_int] * 5 + [_c_void_p] * 6,
+    "epnet_gemm_tf32x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
 }
 
 

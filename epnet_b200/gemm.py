@@ -1,0 +1,59 @@
+"""Host side of the tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu): weight packing and the launch wrapper."""
+import torch
+
+from . import pointnet2_cuda as pc
+from ._lib import LIB
+
+BK = 32
+
+
+def choose_bn(n):
+    """Output-channel tile: one tile of round_up(N,16) columns up to 256, else equal tiles <= 256."""
+    tiles = (n + 255) // 256
+    per = (n + tiles - 1) // tiles
+    return ((per + 15) // 16) * 16
+
+
+class PackedLinear:
+    """W (N,K) fp32 [+ bias (N)] -> the shared-memory image the MMA consumes.
+
+    Per n-tile (BN rows) and k-block (32 columns) two planes, hi and lo, each BN x 128 bytes: K-major rows, grouped in
+    8-row atoms of 1024 B, 16-byte chunk c of row r stored at chunk position c ^ (r % 8) (SWIZZLE_128B).
+    hi = w with the 13 low mantissa bits cleared (exact TF32), lo = w - hi (exact in fp32)."""
+
+    def __init__(self, weight, bias=None):
+        w = weight.detach().float().contiguous()
+        dev = w.device
+        self.N, self.K = w.shape
+        self.BN = choose_bn(self.N)
+        self.n_tiles = (self.N + self.BN - 1) // self.BN
+        self.n_kblocks = (self.K + BK - 1) // BK
+        npad, kpad = self.n_tiles * self.BN, self.n_kblocks * BK
+        wp = torch.zeros(npad, kpad, device=dev)
+        wp[:self.N, :self.K] = w
+        hi = (wp.view(torch.int32) & -8192).view(torch.float32)  # 0xffffe000
+        lo = wp - hi
+        planes = torch.stack([hi, lo])                                    # (2, npad, kpad)
+        planes = planes.view(2, self.n_tiles, self.BN, self.n_kblocks, 8, 4)  # k = kb*32 + c*4 + e
+        planes = planes.permute(1, 3, 0, 2, 4, 5).contiguous()              # (tile, kb, plane, row, c, e)
+        r = torch.arange(self.BN, device=dev) % 8
+        c = torch.arange(8, device=dev)
+        src_chunk = (c[None, :] ^ r[:, None])                               # stored position p holds chunk p ^ (r%8)
+        idx = src_chunk[None, None, None, :, :, None].expand(self.n_tiles, self.n_kblocks, 2, self.BN, 8, 4)
+        self.wpack = torch.gather(planes, 4, idx).contiguous()
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+
+    def __call__(self, x, relu=True, pool=1, out=None):
+        """x (..., K) point-major rows (last dim contiguous) -> (rows / pool, N)"""
+        assert x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1
+        x2 = x.reshape(-1, x.shape[-1]) if x.is_contiguous() else x
+        assert x2.dim() == 2
+        L, ldx = x2.shape[0], x2.stride(0)
+        assert x2.shape[1] >= self.K
+        if out is None:
+            out = torch.empty((L // pool, self.N), dtype=torch.float32, device=x.device)
+        assert out.stride(-1) == 1
+        ldy = out.stride(0)
+        pc._call("gemm_tf32x3", LIB.epnet_gemm_tf32x3, x2, L, self.K, self.N, x2.data_ptr(), ldx, self.wpack.data_ptr(), self.BN,
+                 None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), pool, out.data_ptr(), ldy)
+        return out

@@ -105,6 +105,15 @@ int epnet_bias_relu_maxpool(int b, int c, int m, int nsample, const float *x, co
 int epnet_three_interpolate_concat(int b, int c2, int m, int n, int c1, const float *known_feats, const int *idx,
                                    const float *dist2, const float *skip_feats, float *out, void *stream);
 
+/* One SharedMLP layer as a tcgen05/TMEM GEMM with fp32-grade accuracy (3xTF32 split), point-major operands:
+ *   y[l / pool][n] = max over pool consecutive rows l of act(sum_k x[l][k] * W[n][k] + bias[n])
+ * x (L, ldx) fp32 rows; wpack = W (N,K) split into TF32 hi/lo parts and pre-swizzled by the host into n-tiles of BN
+ * rows x k-blocks of 32 (epnet_b200/gemm.py:pack_weights); bias (N) or NULL; relu 0/1; pool in {1,2,4,8,16,32} (the
+ * nsample max-pool of pointnet2_modules.py:59-61 fused into the epilogue); y (L / pool, ldy).
+ * Replaces the Conv2d(1x1)+BatchNorm(eval)+ReLU units of pytorch_utils.py:20-32 (BN folded into W and bias). */
+int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
+                      int pool, float *y, int ldy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,55 @@
+"""tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu) against a float64 reference: fp32-grade accuracy (the tolerance a plain
+TF32 GEMM fails by two orders of magnitude), bias/ReLU/max-pool epilogues, ragged L / K / N."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, b, relu, pool):
+    y = x.double() @ w.double().t()
+    if b is not None:
+        y = y + b.double()
+    if relu:
+        y = y.clamp_min(0)
+    if pool > 1:
+        y = y.view(-1, pool, y.shape[-1]).max(dim=1).values
+    return y
+
+
+@pytest.mark.parametrize("L,K,N,relu,pool", [
+    (128, 32, 16, False, 1), (256, 32, 16, True, 1), (1000, 99, 64, True, 1), (4096, 259, 196, True, 1), (512, 1536, 512, True, 1),
+    (4096, 6, 32, True, 16), (2048, 99, 128, True, 32), (384, 515, 384, False, 1), (96, 64, 96, True, 2), (33, 35, 17, False, 1),
+])
+def test_gemm_matches_fp64(L, K, N, relu, pool):
+    from epnet_b200.gemm import PackedLinear
+    g = torch.Generator(device="cpu").manual_seed(L * 7 + K)
+    x = torch.randn(L, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    lin = PackedLinear(w, b)
+    y = lin(x, relu=relu, pool=pool)
+    torch.cuda.synchronize()
+    want = _ref(x, w, b, relu, pool)
+    assert y.shape == want.shape
+    err = (y.double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 2e-6 * scale + 1e-6, "max abs err %.3e (scale %.3e)" % (err, scale)
+    # the same product in plain TF32 is ~1e-3: make sure the test would notice a missing correction term
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tf32 = (x @ w.t() + b)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if K >= 64 and pool == 1 and not relu:
+        assert (tf32.double() - want).abs().max().item() > 20 * err
+
+
+def test_gemm_strided_input_and_output():
+    from epnet_b200.gemm import PackedLinear
+    x_full = torch.randn(640, 72, device="cuda")
+    w = torch.randn(40, 67, device="cuda") * 0.1
+    lin = PackedLinear(w, None)
+    out_full = torch.zeros(640, 100, device="cuda")
+    lin(x_full[:, :67], relu=False, out=out_full[:, 8:48])
+    want = x_full[:, :67].double() @ w.double().t()
+    assert (out_full[:, 8:48].double() - want).abs().max().item() < 1e-5
+    assert out_full[:, :8].abs().max().item() == 0 and out_full[:, 48:].abs().max().item() == 0
