@@ -230,3 +230,181 @@ EPNET_API int epnet_three_interpolate_concat(int b, int c2, int m, int n, int c1
                                                                                    c1 ? skip_feats : nullptr, out, vec_ok);
     EPNET_RETURN_LAUNCH_STATUS();
 }
+
+// =================================================================================================
+// Point-major variants: rows are points (or (centre,sample) pairs), channels are contiguous.  This is the
+// layout the tcgen05 GEMM (gemm_tf32x3.cu) consumes as its K-major A operand, and it turns every indexed
+// gather into a contiguous C*4-byte row read (full 32-byte sectors) instead of C separate 4-byte reads
+// from a channel-major (B,C,N) tensor -- the reference layout's gathers are L2-sector-bound at 1/8 efficiency.
+// =================================================================================================
+namespace epnet {
+
+// out[(b,p,s)][0..C) = feats[b, idx[b,p,s], 0..C) ; out[..][C..C+3) = xyz[b, idx] - new_xyz[b,p]
+// One thread per (row, 16-byte column chunk).
+__global__ void __launch_bounds__(256)
+group_concat_pm_kernel(int c, int n, int m, int ns, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                       const float *__restrict__ feats, int ldf, const int *__restrict__ idx, float *__restrict__ out, int ldo,
+                       long long rows_total, int chunks, int vec_ok)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_total * chunks) return;
+    const long long row = t / chunks;
+    const int ch = (int)(t - row * chunks);
+    const long long per_scene = (long long)m * ns;
+    const int scene = (int)(row / per_scene);
+    const long long e = row - (long long)scene * per_scene;
+    const int p = (int)(e / ns);
+    const int src = __ldg(idx + row);
+    const int k0 = ch * 4;
+    float v[4];
+    if (vec_ok && k0 + 4 <= c) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(feats + ((size_t)scene * n + src) * ldf + k0));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            if (k < c) v[j] = __ldg(feats + ((size_t)scene * n + src) * ldf + k);
+            else if (k < c + 3) v[j] = __fsub_rn(__ldg(xyz + ((size_t)scene * n + src) * 3 + (k - c)), __ldg(new_xyz + ((size_t)scene * m + p) * 3 + (k - c)));
+            else v[j] = 0.f;
+        }
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + k0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// out[(b,i)][0..C2) = sum_k w_k * known[b, idx[b,i,k], :] ; out[..][C2..C2+C1) = skip[b,i,:]
+__global__ void __launch_bounds__(256)
+three_interpolate_concat_pm_kernel(int c2, int m, int n, int c1, const float *__restrict__ known, int ldk, const int *__restrict__ idx,
+                                   const float *__restrict__ dist2, const float *__restrict__ skip, int lds, float *__restrict__ out,
+                                   int ldo, long long rows_total, int chunks)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_total * chunks) return;
+    const long long row = t / chunks;
+    const int ch = (int)(t - row * chunks);
+    const int scene = (int)(row / n);
+    const int k0 = ch * 4;
+    float4 o;
+    if (k0 < c2) {
+        const int i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3)), 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 1)), 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 2)), 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+        const float *kb = known + (size_t)scene * m * ldk + k0;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i0 * ldk));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i1 * ldk));
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i2 * ldk));
+        o.x = __fmaf_rn(w2, c.x, __fmaf_rn(w0, a.x, __fmul_rn(w1, b.x)));
+        o.y = __fmaf_rn(w2, c.y, __fmaf_rn(w0, a.y, __fmul_rn(w1, b.y)));
+        o.z = __fmaf_rn(w2, c.z, __fmaf_rn(w0, a.z, __fmul_rn(w1, b.z)));
+        o.w = __fmaf_rn(w2, c.w, __fmaf_rn(w0, a.w, __fmul_rn(w1, b.w)));
+    } else {
+        o = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * lds + (k0 - c2)));
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + k0) = o;
+}
+
+// out[(b,i)][col_off + ch] = bilinear(fmap[b,ch], xy[b,i]); one thread per (point, 4 channels)
+__device__ __forceinline__ void pm_taps(float gx, float gy, int h, int w, int align_corners, int *o, float *wt)
+{
+    float ix, iy;
+    if (align_corners) {
+        ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(w - 1));
+        iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(h - 1));
+    } else {
+        ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), (float)w, -1.f), 0.5f);
+        iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), (float)h, -1.f), 0.5f);
+    }
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);
+    const float wx0 = __fsub_rn((float)x1, ix), wy0 = __fsub_rn((float)y1, iy);
+    const bool xin0 = x0 >= 0 && x0 < w, xin1 = x1 >= 0 && x1 < w, yin0 = y0 >= 0 && y0 < h, yin1 = y1 >= 0 && y1 < h;
+    wt[0] = (xin0 && yin0) ? __fmul_rn(wx0, wy0) : 0.f; o[0] = (xin0 && yin0) ? y0 * w + x0 : 0;
+    wt[1] = (xin1 && yin0) ? __fmul_rn(wx1, wy0) : 0.f; o[1] = (xin1 && yin0) ? y0 * w + x1 : 0;
+    wt[2] = (xin0 && yin1) ? __fmul_rn(wx0, wy1) : 0.f; o[2] = (xin0 && yin1) ? y1 * w + x0 : 0;
+    wt[3] = (xin1 && yin1) ? __fmul_rn(wx1, wy1) : 0.f; o[3] = (xin1 && yin1) ? y1 * w + x1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+grid_gather_pm_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, const float *__restrict__ xy, int align_corners,
+                      float *__restrict__ out, int ldo, long long rows_total, int chunks)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_total * chunks) return;
+    const long long row = t / chunks;
+    const int ch0 = (int)(t - row * chunks) * 4;
+    const int scene = (int)(row / n);
+    const float2 g = __ldg(reinterpret_cast<const float2 *>(xy + row * 2));
+    int o[4];
+    float wt[4];
+    pm_taps(g.x, g.y, h, w, align_corners, o, wt);
+    const size_t plane = (size_t)h * w;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int chn = ch0 + j;
+        if (chn < c) {
+            const float *p = fmap + ((size_t)scene * c + chn) * plane;
+            float acc = __fmul_rn(__ldg(p + o[0]), wt[0]);
+            acc = __fmaf_rn(__ldg(p + o[1]), wt[1], acc);
+            acc = __fmaf_rn(__ldg(p + o[2]), wt[2], acc);
+            acc = __fmaf_rn(__ldg(p + o[3]), wt[3], acc);
+            v[j] = acc;
+        } else {
+            v[j] = 0.f;
+        }
+    }
+    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+}  // namespace epnet
+
+EPNET_API int epnet_group_concat_pm(int b, int c, int n, int m, int nsample, const float *xyz, const float *new_xyz, const float *feats,
+                                    int ldf, const int *idx, float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c < 0 || n < 0 || m < 0 || nsample < 0 || !xyz || !new_xyz || !idx || !out || (c > 0 && !feats)) return EPNET_ERR_BAD_ARG;
+    if (ldo < c + 3 || (ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * m * nsample;
+    if (rows == 0) return EPNET_OK;
+    const int chunks = (c + 3 + 3) / 4;
+    const int vec_ok = c > 0 && (ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
+    const long long threads = rows * chunks;
+    group_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, n, m, nsample, xyz, new_xyz, feats, ldf, idx,
+                                                                                            out, ldo, rows, chunks, vec_ok);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int c1, const float *known, int ldk, const int *idx,
+                                                const float *dist2, const float *skip, int lds, float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c2 <= 0 || c1 < 0 || m < 0 || n < 0 || !known || !idx || !dist2 || !out || (c1 > 0 && !skip)) return EPNET_ERR_BAD_ARG;
+    if ((c2 & 3) || (c1 & 3) || (ldk & 3) || (ldo & 3) || (c1 > 0 && (lds & 3)) || ldo < c1 + c2) return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(known) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(skip)) & 15) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * n;
+    if (rows == 0) return EPNET_OK;
+    const int chunks = (c1 + c2) / 4;
+    const long long threads = rows * chunks;
+    three_interpolate_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2, m, n, c1, known, ldk, idx, dist2,
+                                                                                                        skip, lds, out, ldo, rows, chunks);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out,
+                                   int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c <= 0 || h <= 0 || w <= 0 || n < 0 || !fmap || !xy || !out) return EPNET_ERR_BAD_ARG;
+    if ((ldo & 3) || ldo < c || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(xy) & 7)) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * n;
+    if (rows == 0) return EPNET_OK;
+    const int chunks = (c + 3) / 4;
+    const long long threads = rows * chunks;
+    grid_gather_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out, ldo,
+                                                                                           rows, chunks);
+    EPNET_RETURN_LAUNCH_STATUS();
+}

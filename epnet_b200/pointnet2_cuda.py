@@ -157,3 +157,21 @@ def three_interpolate_concat_wrapper(b, c2, m, n, c1, known_feats, idx, dist2, s
     _call("three_interpolate_concat", LIB.epnet_three_interpolate_concat, known_feats, b, c2, m, n, c1,
           _f(known_feats, "known_feats"), _i(idx, "idx"), _f(dist2, "dist2"), _opt(skip_feats, torch.float32, "skip_feats"),
           _f(out, "out"))
+
+
+def group_concat_pm_wrapper(b, c, n, m, nsample, xyz, new_xyz, feats_pm, idx, out):
+    """out (B*M*nsample, ldo) rows = [features (C) | xyz - centre (3) | pad]; feats_pm (B,N,C) point-major or None."""
+    ldf = 0 if feats_pm is None else feats_pm.stride(-2)
+    _call("group_concat_pm", LIB.epnet_group_concat_pm, xyz, b, c, n, m, nsample, _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
+          _opt(feats_pm, torch.float32, "feats_pm"), ldf, _i(idx, "idx"), out.data_ptr(), out.stride(0))
+
+
+def three_interpolate_concat_pm_wrapper(b, c2, m, n, c1, known_pm, idx, dist2, skip_pm, out):
+    _call("three_interpolate_concat_pm", LIB.epnet_three_interpolate_concat_pm, known_pm, b, c2, m, n, c1, known_pm.data_ptr(),
+          known_pm.stride(-2), _i(idx, "idx"), _f(dist2, "dist2"), None if skip_pm is None else skip_pm.data_ptr(),
+          0 if skip_pm is None else skip_pm.stride(-2), out.data_ptr(), out.stride(0))
+
+
+def grid_gather_pm_wrapper(b, c, h, w, n, fmap, xy, align_corners, out):
+    _call("grid_gather_pm", LIB.epnet_grid_gather_pm, fmap, b, c, h, w, n, _f(fmap, "feature_map"), _f(xy, "xy"),
+          int(bool(align_corners)), out.data_ptr(), out.stride(0))

@@ -18,6 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
+from .gemm import PackedLinear
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -72,8 +73,42 @@ class _Fusion:
         return out
 
 
+
+class _FusionPM:
+    """Atten_Fusion_Conv / Fusion_Conv on point-major rows with tcgen05 GEMMs.  `cat` is a (rows, 2*Cp) buffer whose left
+    half already holds the point features (written there by the producing GEMM) -- the concat costs nothing."""
+
+    def __init__(self, mod):
+        self.attention = hasattr(mod, "IA_Layer")
+        if self.attention:
+            ia = mod.IA_Layer
+            self.fc1 = PackedLinear(ia.fc1.weight, ia.fc1.bias + ia.fc2.bias)  # the two biases are summed before tanh
+            self.fc2 = PackedLinear(ia.fc2.weight, None)
+            self.w3, self.b3 = ia.fc3.weight.detach().reshape(-1).contiguous(), ia.fc3.bias.detach()
+            conv, bn = ia.conv1[0], ia.conv1[1]
+            self.conv = PackedLinear(*_fold_bn(conv.weight.squeeze(-1), conv.bias, bn))
+        self.fuse = PackedLinear(*_fold_bn(mod.conv1.weight.squeeze(-1), mod.conv1.bias, mod.bn1))
+        self.cp = mod.conv1.out_channels
+        self.cat_width = mod.conv1.in_channels
+
+    def __call__(self, cat, img, out=None):
+        """cat (rows, Cp + Ci') with point features in [:, :Cp]; img (rows, Ci) gathered image features -> (rows, Cp)"""
+        cp = self.cp
+        if self.attention:
+            point = cat[:, :cp]
+            r = self.fc1(img, relu=False) + self.fc2(point, relu=False)
+            att = torch.sigmoid(torch.tanh(r) @ self.w3 + self.b3)  # (rows,)
+            img_new = self.conv(img, relu=True)
+            torch.mul(img_new, att[:, None], out=cat[:, cp:])
+        else:
+            cat[:, cp:].copy_(img)
+        return self.fuse(cat, relu=True, out=out)
+
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True):
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm"):
+        """layout "pm": point-major activations + tcgen05 3xTF32 GEMMs (default); "cm": channel-major + cuBLAS."""
+        assert layout in ("pm", "cm")
+        self.layout = layout
         if model.training:
             raise RuntimeError("BackboneRunner folds BatchNorm: call model.eval() first (train mode: use model(...) itself)")
         c = model.config
@@ -105,6 +140,9 @@ class BackboneRunner:
                 self.final_fusion = _Fusion(model.final_fusion_img_point)
                 wq, bq = _fold_bn(model.image_fusion_conv.weight.flatten(1), model.image_fusion_conv.bias, model.image_fusion_bn)
                 self.img_fuse_w, self.img_fuse_b = wq.view_as(model.image_fusion_conv.weight).contiguous(), bq
+
+            if layout == "pm":
+                self._build_pm()
 
         self.s_fps = torch.cuda.Stream(device=device)
         self.s_img = torch.cuda.Stream(device=device)
@@ -139,6 +177,7 @@ class BackboneRunner:
         f32 = dict(dtype=torch.float32, device=dev)
         xyz0 = self.points
         xyn = self.xy / self._xy_scale * 2.0 - 1.0 if c.li_fusion else None  # pointnet2_msg.py:208-210
+        pm = self.layout == "pm"
 
         # ---- FPS chain of all levels (coordinates only) on its own stream ----
         ready = torch.cuda.Event()
@@ -181,7 +220,13 @@ class BackboneRunner:
                 img_fusion_done = torch.cuda.Event()
                 img_fusion_done.record(self.s_img)
 
-        # ---- point stream ----
+        if pm:
+            feats = self._point_stream_pm(main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn)
+            main.wait_stream(self.s_fps)
+            main.wait_stream(self.s_img)
+            return xyz0, feats
+
+        # ---- point stream (channel-major, cuBLAS) ----
         l_feat = [None]
         for k, (npoint, scales) in enumerate(self.sa):
             main.wait_event(fps_done[k])
@@ -228,6 +273,86 @@ class BackboneRunner:
         main.wait_stream(self.s_fps)
         main.wait_stream(self.s_img)
         return xyz0, feats
+
+
+    # ------------------------------------------------------------------------------------ point-major path
+    def _build_pm(self):
+        """tcgen05 GEMM parameters: BN folded, weights split/swizzled once (gemm.PackedLinear)."""
+        self.sa_pm = []
+        for npoint, scales in self.sa:
+            packed = []
+            for radius, ns, layers in scales:
+                w0, b0 = layers[0]
+                w0 = torch.cat([w0[:, 3:], w0[:, :3]], dim=1)  # group_concat_pm puts the 3 re-centred xyz channels last
+                lins = [PackedLinear(w0, b0)] + [PackedLinear(w, b) for w, b in layers[1:]]
+                packed.append((radius, ns, lins))
+            self.sa_pm.append((npoint, packed))
+        self.fp_pm = [[PackedLinear(w, b) for w, b in layers] for layers in self.fp]
+        if self.cfg.li_fusion:
+            self.fusion_pm = [_FusionPM(m) for m in self.model.Fusion_Conv]
+            self.final_fusion_pm = _FusionPM(self.model.final_fusion_img_point)
+
+    def _point_stream_pm(self, main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn):
+        c, B, N, dev = self.cfg, self.B, self.N, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        l_feat = [None]  # (B*n_k, C_k) point-major
+        for k, (npoint, scales) in enumerate(self.sa_pm):
+            main.wait_event(fps_done[k])
+            xyz, new_xyz, feats = l_xyz[k], l_xyz[k + 1], l_feat[k]
+            n = xyz.shape[1]
+            cin = 0 if feats is None else feats.shape[1]
+            ctot = sum(lins[-1].N for _, _, lins in scales)
+            width = self.fusion_pm[k].cat_width if c.li_fusion else ctot
+            cat = torch.empty((B * npoint, width), **f32)  # [ SA output | (attended) image features ]
+            c_off = 0
+            for radius, ns, lins in scales:
+                bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
+                pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
+                kp = (cin + 3 + 3) // 4 * 4
+                x = torch.empty((B * npoint * ns, kp), **f32)
+                pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, None if feats is None else feats.view(B, n, cin), bidx, x)
+                for lin in lins[:-1]:
+                    x = lin(x, relu=True)
+                lins[-1](x, relu=True, pool=ns, out=cat[:, c_off:c_off + lins[-1].N])  # ReLU + max over nsample in the epilogue
+                c_off += lins[-1].N
+            if c.li_fusion:
+                main.wait_event(img_done[k])
+                img = imgs[k]
+                ci = img.shape[1]
+                g = torch.empty((B * npoint, (ci + 3) // 4 * 4), **f32)
+                pc.grid_gather_pm_wrapper(B, ci, img.shape[2], img.shape[3], npoint, img, l_xy[k + 1], c.align_corners, g)
+                l_feat.append(self.fusion_pm[k](cat, g[:, :ci]))
+            else:
+                l_feat.append(cat)
+
+        for i in range(-1, -(len(self.fp_pm) + 1), -1):
+            unknown, known = l_xyz[i - 1], l_xyz[i]
+            n, m = unknown.shape[1], known.shape[1]
+            skip, kf = l_feat[i - 1], l_feat[i]
+            c1 = 0 if skip is None else skip.shape[1]
+            c2 = kf.shape[1]
+            dist2 = torch.empty((B, n, 3), **f32)
+            idx3 = torch.empty((B, n, 3), dtype=torch.int32, device=dev)
+            pc.three_nn_wrapper(B, n, m, unknown, known, dist2, idx3)
+            x = torch.empty((B * n, c2 + c1), **f32)
+            pc.three_interpolate_concat_pm_wrapper(B, c2, m, n, c1, kf, idx3, dist2, skip, x)
+            lins = self.fp_pm[i]
+            last_out = None
+            if i - 1 == -(len(self.fp_pm) + 1) and c.li_fusion:  # level 0: write straight into the final fusion's concat buffer
+                final_cat = torch.empty((B * n, self.final_fusion_pm.cat_width), **f32)
+                last_out = final_cat[:, :lins[-1].N]
+            for lin in lins[:-1]:
+                x = lin(x, relu=True)
+            l_feat[i - 1] = lins[-1](x, relu=True, out=last_out)
+
+        feats = l_feat[0]
+        if c.li_fusion:
+            main.wait_event(img_fusion_done)
+            ci = img_fusion.shape[1]
+            g = torch.empty((B * N, (ci + 3) // 4 * 4), **f32)
+            pc.grid_gather_pm_wrapper(B, ci, img_fusion.shape[2], img_fusion.shape[3], N, img_fusion, xyn, c.align_corners, g)
+            feats = self.final_fusion_pm(final_cat, g[:, :ci])
+        return feats.view(B, N, -1).transpose(1, 2).contiguous()  # interface layout (B, C, N)
 
     # ------------------------------------------------------------------------------------ graph
     def _capture(self):

@@ -58,12 +58,12 @@ def test_module_path_equals_reference_kernels():
     _close(f_o, f_r, 1e-5)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_runner_equals_module_path(use_graph):
+@pytest.mark.parametrize("layout,use_graph", [("pm", False), ("pm", True), ("cm", True)])
+def test_runner_equals_module_path(layout, use_graph):
     from epnet_b200 import scenes
     _strict_fp32()
     ours = _models()
-    runner = ours.make_runner(2, 16384, torch.device("cuda"), use_graph=use_graph)
+    runner = ours.make_runner(2, 16384, torch.device("cuda"), use_graph=use_graph, layout=layout)
     for seed in (1000, 1020):
         data = {k: v.cuda() for k, v in scenes.batch(seed, 2, 16384).items()}
         with torch.no_grad():
@@ -74,8 +74,11 @@ def test_runner_equals_module_path(use_graph):
         assert torch.equal(data["xy"], xy_before)  # the runner does not touch the caller's xy
         assert torch.equal(xyz_r, xyz_m)
         assert f_r.shape == f_m.shape == (2, 128, 16384)
-        # BN folding and GEMM re-association move results by a few fp32 ulps per layer
-        _close(f_r, f_m, 2e-5)
+        # BN folding and GEMM re-association move results by a few fp32 ulps per layer; the tcgen05 3xTF32 GEMMs of the
+        # point-major path add up to ~8e-6 per layer at K=1536 (tests/test_gemm_gpu.py)
+        err = (f_r - f_m).abs().max().item() / f_m.abs().max().item()
+        print("runner[%s] vs module path: max abs err / output scale = %.2e" % (layout, err))
+        _close(f_r, f_m, 2e-5 if layout == "cm" else 5e-5)
 
 
 def test_state_dict_keys_match_reference_naming():
