@@ -95,7 +95,40 @@ def sweep_rooflines(device, peak):
     xy = (torch.rand(1, n, 2, generator=g) * 2 - 1).to(device)
     out = torch.empty(1, C, n, device=device)
     add("grid_gather_bilinear", (1, C, H, W, n), lambda: pc.grid_gather_bilinear_wrapper(1, C, H, W, n, fmap, xy, False, out))
+    # point-major fused kernels (the runner's path): a gathered point is one contiguous row
+    C, N, M, ns = 128, 65536, 16384, 32
+    xyz = torch.randn(1, N, 3, device=device)
+    new_xyz = xyz[:, :M].contiguous()
+    feats_pm = torch.randn(1, N, C, device=device)
+    idx = torch.randint(0, N, (1, M, ns), generator=g).int().to(device)
+    kp = (C + 3 + 3) // 4 * 4
+    out = torch.empty(M * ns, kp, device=device)
+    t = _event_time(lambda: pc.group_concat_pm_wrapper(1, C, N, M, ns, xyz, new_xyz, feats_pm, idx, out))
+    by = 4 * C * min(N, M * ns) + 4 * M * ns + 4 * kp * M * ns
+    rows.append({"op": "group_concat_pm", "shape": [1, C, N, M, ns], "us": round(t * 1e6, 1), "algorithmic_mb": round(by / 1e6, 1),
+                 "achieved_gbs": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak, 3)})
+    C2, m, n = 256, 32768, 131072
+    known = torch.randn(1, m, C2, device=device)
+    idx3 = torch.randint(0, m, (1, n, 3), generator=g).int().to(device)
+    d2 = torch.rand(1, n, 3, generator=g).to(device)
+    out = torch.empty(n, C2, device=device)
+    t = _event_time(lambda: pc.three_interpolate_concat_pm_wrapper(1, C2, m, n, 0, known, idx3, d2, None, out))
+    by = 4 * C2 * min(m, 3 * n) + 24 * n + 4 * C2 * n
+    rows.append({"op": "three_interpolate_concat_pm", "shape": [1, C2, m, n], "us": round(t * 1e6, 1), "algorithmic_mb": round(by / 1e6, 1),
+                 "achieved_gbs": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak, 3)})
     return rows
+
+
+def gemm_tensor_rate(device):
+    """tcgen05 3xTF32 GEMM at a large shared-MLP shape: fp32-equivalent TFLOP/s (2*L*K*N / time); the tensor pipe executes 3x that in TF32."""
+    from epnet_b200.gemm import PackedLinear
+    L, K, N = 65536, 512, 256
+    x = torch.randn(L, K, device=device)
+    lin = PackedLinear(torch.randn(N, K, device=device) / K ** 0.5, torch.zeros(N, device=device))
+    out = torch.empty(L, N, device=device)
+    t = _event_time(lambda: lin(x, relu=True, out=out))
+    return {"kernel": "gemm_tf32x3", "shape": [L, K, N], "us": round(t * 1e6, 1), "fp32_equiv_tflops": round(2.0 * L * K * N / t / 1e12, 1),
+            "tf32_mma_tflops": round(6.0 * L * K * N / t / 1e12, 1)}
 
 
 def measure(model, runner, dev_pool, device, world):
@@ -143,4 +176,5 @@ def measure(model, runner, dev_pool, device, world):
         out["fps_ns_per_iteration"] = {"%d->%d" % (k[1][1], k[1][2]): round(v[0] / v[1] / max(k[1][2] - 1, 1) * 1e9, 1) for k, v in fps}
     if world == 1:
         out["op_rooflines"] = sweep_rooflines(device, peak)
+        out["gemm_tensor_rate"] = gemm_tensor_rate(device)
     return out

@@ -72,6 +72,20 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// 32 lanes x 32 consecutive columns of the accumulator -> 32 registers per thread (thread = lane = tile row); no wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
 struct GemmArgs {
     const float *x;        // (L, ldx) rows; columns >= K are never read
     const float *wpack;    // packed weights: [n_tile][k_block][hi|lo][BN rows * 128 B]
@@ -87,12 +101,13 @@ struct GemmArgs {
     int x_vec_ok;          // x base 16-byte aligned and ldx % 4 == 0
 };
 
-__global__ void __launch_bounds__(kGmThreads, 1)
+__global__ void __launch_bounds__(kGmThreads, 2)
 gemm_tf32x3_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t gm_smem[];
     __shared__ __align__(8) uint64_t full_a[kGmMaxStages], full_b[kGmMaxStages], empty[kGmMaxStages], accum_bar;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kGmBM;
@@ -104,8 +119,12 @@ gemm_tf32x3_kernel(const GemmArgs a)
     // stage layout: [A_hi | A_lo | B_hi | B_lo], every plane 1024-byte aligned (BN % 8 == 0)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
 
+    // two fp32 accumulators: columns [0,BN) take hi*hi, columns [BNP, BNP+BN) take the two correction terms.  The tensor
+    // core's accumulate truncates, so its error grows with the number of read-modify-writes; keeping the small terms apart
+    // leaves the main accumulator with K/8 updates instead of 3K/8 and the sum is formed once, in fp32 RN, in the epilogue.
+    const uint32_t BNP = (uint32_t)((BN + 31) & ~31);
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    while (tmem_cols < 2 * BNP) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < a.stages; ++s) {
@@ -121,6 +140,10 @@ gemm_tf32x3_kernel(const GemmArgs a)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int j = tid; j < 256 + 32; j += kGmThreads) {
+        const int n = ntile * BN + j;
+        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -130,29 +153,39 @@ gemm_tf32x3_kernel(const GemmArgs a)
         // ===================== X producers =====================
         const int chunk = tid & 7;          // 16-byte chunk of the 128-byte k-row
         const int rbase = tid >> 3;         // 0..15; rows rbase + 16*i
-        for (int kb = 0; kb < a.n_kblocks; ++kb) {
-            const int s = kb % a.stages;
-            const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
-            uint8_t *a_hi = smem + (size_t)s * stage_bytes;
-            uint8_t *a_lo = a_hi + a_bytes;
+        // global loads of k-block kb+1 are issued before k-block kb is converted and stored: one block of latency is hidden
+        auto load_block = [&](int kb, float4 (&v)[8]) {
             const int k0 = kb * kGmBK + chunk * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                const int row = row0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < a.L) {
+                const int row = row0 + rbase + 16 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < a.L && k0 < a.K) {
                     const float *src = a.x + (size_t)row * a.ldx + k0;
                     if (a.x_vec_ok && k0 + 4 <= a.K) {
-                        v = __ldg(reinterpret_cast<const float4 *>(src));
+                        v[i] = __ldg(reinterpret_cast<const float4 *>(src));
                     } else {
-                        if (k0 + 0 < a.K) v.x = __ldg(src + 0);
-                        if (k0 + 1 < a.K) v.y = __ldg(src + 1);
-                        if (k0 + 2 < a.K) v.z = __ldg(src + 2);
-                        if (k0 + 3 < a.K) v.w = __ldg(src + 3);
+                        v[i].x = __ldg(src + 0);
+                        if (k0 + 1 < a.K) v[i].y = __ldg(src + 1);
+                        if (k0 + 2 < a.K) v[i].z = __ldg(src + 2);
+                        if (k0 + 3 < a.K) v[i].w = __ldg(src + 3);
                     }
                 }
+            }
+        };
+        float4 cur[8], nxt[8];
+        load_block(0, cur);
+        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            const int s = kb % a.stages;
+            const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
+            if (kb + 1 < a.n_kblocks) load_block(kb + 1, nxt);
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t *a_hi = smem + (size_t)s * stage_bytes;
+            uint8_t *a_lo = a_hi + a_bytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const float4 v = cur[i];
                 uint4 hi, lo;
                 hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
                 hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
@@ -164,6 +197,8 @@ gemm_tf32x3_kernel(const GemmArgs a)
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(&full_a[s]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
 
         // ===================== epilogue =====================
@@ -172,57 +207,59 @@ gemm_tf32x3_kernel(const GemmArgs a)
         const int r = warp * 32 + lane;  // TMEM lane == tile row
         const int row = row0 + r;
         const int pool = a.pool;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t v[16];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32], w[32];
             const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                "tcgen05.wait::ld.sync.aligned;\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr)
-                : "memory");
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + BNP, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int ncols = min(32, BN - c0);
             const int n0 = ntile * BN + c0;
-            float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float f = __uint_as_float(v[j]);
-                if (a.bias && n0 + j < a.N) f += __ldg(a.bias + n0 + j);
+            for (int j = 0; j < 32; ++j) {
+                float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) + bias_s[c0 + j];
                 if (a.relu) f = fmaxf(f, 0.f);
-                o[j] = f;
+                v[j] = __float_as_uint(f);
             }
             if (pool == 1) {
                 if (row < a.L) {
                     float *dst = a.y + (size_t)row * a.ldy + n0;
-                    if (n0 + 16 <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+                    if (n0 + ncols <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < ncols) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < a.N) dst[j] = o[j];
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols && n0 + j < a.N) dst[j] = __uint_as_float(v[j]);
                     }
                 }
             } else {
-                // max over `pool` consecutive rows.  Outputs are >= 0 after ReLU or arbitrary otherwise: use an order-preserving
-                // float->uint map so one redux.sync.max per column does the lane reduction.
+                // max over `pool` consecutive rows (= lanes): order-preserving float->uint map, then an xor-butterfly inside
+                // aligned groups of `pool` lanes; each step runs over all 32 columns (independent shuffles in flight)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    uint32_t u = __float_as_uint(row < a.L ? o[j] : -__int_as_float(0x7f800000));
-                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-                    if (pool >= 32) {
-                        u = warp_max_u32(u);
-                    } else {  // pool in {2,4,8,16}: butterfly inside aligned groups of `pool` lanes
-                        for (int d = 1; d < pool; d <<= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, d));
-                    }
-                    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-                    o[j] = __uint_as_float(u);
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t u = row < a.L ? v[j] : 0xff800000u;  // -inf for rows past the end
+                    v[j] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
                 }
-                if ((lane % pool) == 0 && row < a.L) {
-                    float *dst = a.y + (size_t)(row / pool) * a.ldy + n0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < a.N) dst[j] = o[j];
+                for (int d = 1; d < 32; d <<= 1) {
+                    if (d < pool) {  // warp-uniform
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], d));
+                    }
+                }
+                // every lane of a group now holds the group's maxima; lane t of the group stores columns j == t (mod pool)
+                if (row < a.L) {
+                    float *dst = a.y + (size_t)(row / pool) * a.ldy + n0;
+                    const int t = lane % pool;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((j % pool) == t && j < ncols && n0 + j < a.N) {
+                            const uint32_t u = v[j];
+                            dst[j] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+                        }
+                    }
                 }
             }
         }
@@ -243,9 +280,9 @@ gemm_tf32x3_kernel(const GemmArgs a)
 #pragma unroll
                 for (int ks = 0; ks < kGmBK / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along the swizzled row
-                    umma_tf32(tmem_acc, d_al + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);  // small terms first
-                    umma_tf32(tmem_acc, d_ah + adv, d_bl + adv, idesc, 1u);
-                    umma_tf32(tmem_acc, d_ah + adv, d_bh + adv, idesc, 1u);
+                    umma_tf32(tmem_acc + BNP, d_al + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
+                    umma_tf32(tmem_acc + BNP, d_ah + adv, d_bl + adv, idesc, 1u);
+                    umma_tf32(tmem_acc, d_ah + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
                 }
                 umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
             }
@@ -293,9 +330,10 @@ EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, co
     a.relu = relu; a.pool = pool;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
     const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)BN * 128;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((100 * 1024) / stage_bytes);  // <= ~100 KB per CTA: two CTAs per SM overlap each other's epilogue
     if (stages > kGmMaxStages) stages = kGmMaxStages;
     if (stages > a.n_kblocks) stages = a.n_kblocks;
+    if (stages < 2 && a.n_kblocks > 1) stages = 2;
     if (stages < 1) stages = 1;
     a.stages = stages;
     const size_t smem = stage_bytes * stages + 1024;

@@ -72,4 +72,4 @@ def test_small_backbone_on_cuda(path):
     np.testing.assert_array_equal(xyz.cpu().numpy(), g["out_xyz"])
     want = g["out_features"]
     err = np.abs(feat.cpu().numpy() - want).max()
-    assert err <= (5e-5 if path == "runner_pm" else 2e-5) * np.abs(want).max(), (err, np.abs(want).max())
+    assert err <= 2e-5 * np.abs(want).max(), (err, np.abs(want).max())
