@@ -239,71 +239,95 @@ EPNET_API int epnet_three_interpolate_concat(int b, int c2, int m, int n, int c1
 // =================================================================================================
 namespace epnet {
 
+// Thread mapping shared by the point-major kernels: a group of G = 2^g lanes (G >= chunks per row, capped at 32) owns one
+// output row and walks its 16-byte chunks; a warp therefore covers 32/G rows, and every gathered row is read as one
+// contiguous run by adjacent lanes.  Row-level quantities (index, weights) are computed once per lane, no 64-bit divides.
+struct PmMap {
+    long long row;   // output row handled by this lane
+    int chunk0;      // first chunk of this lane
+    int step;        // chunk stride (= G)
+};
+__device__ __forceinline__ PmMap pm_map(int group_shift)
+{
+    const int G = 1 << group_shift;
+    const long long lane_global = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PmMap m;
+    m.row = lane_global >> group_shift;
+    m.chunk0 = (int)(lane_global & (G - 1));
+    m.step = G;
+    return m;
+}
+
 // out[(b,p,s)][0..C) = feats[b, idx[b,p,s], 0..C) ; out[..][C..C+3) = xyz[b, idx] - new_xyz[b,p]
-// One thread per (row, 16-byte column chunk).
 __global__ void __launch_bounds__(256)
 group_concat_pm_kernel(int c, int n, int m, int ns, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                        const float *__restrict__ feats, int ldf, const int *__restrict__ idx, float *__restrict__ out, int ldo,
-                       long long rows_total, int chunks, int vec_ok)
+                       long long rows_total, int chunks, int vec_ok, int group_shift)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rows_total * chunks) return;
-    const long long row = t / chunks;
-    const int ch = (int)(t - row * chunks);
-    const long long per_scene = (long long)m * ns;
-    const int scene = (int)(row / per_scene);
-    const long long e = row - (long long)scene * per_scene;
-    const int p = (int)(e / ns);
-    const int src = __ldg(idx + row);
-    const int k0 = ch * 4;
-    float v[4];
-    if (vec_ok && k0 + 4 <= c) {
-        const float4 f = __ldg(reinterpret_cast<const float4 *>(feats + ((size_t)scene * n + src) * ldf + k0));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-    } else {
+    const PmMap map = pm_map(group_shift);
+    if (map.row >= rows_total) return;
+    const int centre = (int)(map.row / ns);            // b*m + p
+    const int scene = centre / m;
+    const int src = __ldg(idx + map.row);
+    const float *frow = feats + ((size_t)scene * n + src) * ldf;
+    const float *prow = xyz + ((size_t)scene * n + src) * 3;
+    const float *crow = new_xyz + (size_t)centre * 3;
+    float *orow = out + (size_t)map.row * ldo;
+    for (int ch = map.chunk0; ch < chunks; ch += map.step) {
+        const int k0 = ch * 4;
+        float4 v;
+        if (vec_ok && k0 + 4 <= c) {
+            v = __ldg(reinterpret_cast<const float4 *>(frow + k0));
+        } else {
+            float e[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = k0 + j;
-            if (k < c) v[j] = __ldg(feats + ((size_t)scene * n + src) * ldf + k);
-            else if (k < c + 3) v[j] = __fsub_rn(__ldg(xyz + ((size_t)scene * n + src) * 3 + (k - c)), __ldg(new_xyz + ((size_t)scene * m + p) * 3 + (k - c)));
-            else v[j] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j;
+                if (k < c) e[j] = __ldg(frow + k);
+                else if (k < c + 3) e[j] = __fsub_rn(__ldg(prow + (k - c)), __ldg(crow + (k - c)));
+                else e[j] = 0.f;
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
         }
+        __stcs(reinterpret_cast<float4 *>(orow + k0), v);  // streamed: consumed once by the GEMM producer
     }
-    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + k0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // out[(b,i)][0..C2) = sum_k w_k * known[b, idx[b,i,k], :] ; out[..][C2..C2+C1) = skip[b,i,:]
 __global__ void __launch_bounds__(256)
 three_interpolate_concat_pm_kernel(int c2, int m, int n, int c1, const float *__restrict__ known, int ldk, const int *__restrict__ idx,
                                    const float *__restrict__ dist2, const float *__restrict__ skip, int lds, float *__restrict__ out,
-                                   int ldo, long long rows_total, int chunks)
+                                   int ldo, long long rows_total, int chunks, int group_shift)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rows_total * chunks) return;
-    const long long row = t / chunks;
-    const int ch = (int)(t - row * chunks);
+    const PmMap map = pm_map(group_shift);
+    if (map.row >= rows_total) return;
+    const long long row = map.row;
     const int scene = (int)(row / n);
-    const int k0 = ch * 4;
-    float4 o;
-    if (k0 < c2) {
-        const int i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
-        const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3)), 1e-8f));
-        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 1)), 1e-8f));
-        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 2)), 1e-8f));
-        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-        const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
-        const float *kb = known + (size_t)scene * m * ldk + k0;
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i0 * ldk));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i1 * ldk));
-        const float4 c = __ldg(reinterpret_cast<const float4 *>(kb + (size_t)i2 * ldk));
-        o.x = __fmaf_rn(w2, c.x, __fmaf_rn(w0, a.x, __fmul_rn(w1, b.x)));
-        o.y = __fmaf_rn(w2, c.y, __fmaf_rn(w0, a.y, __fmul_rn(w1, b.y)));
-        o.z = __fmaf_rn(w2, c.z, __fmaf_rn(w0, a.z, __fmul_rn(w1, b.z)));
-        o.w = __fmaf_rn(w2, c.w, __fmaf_rn(w0, a.w, __fmul_rn(w1, b.w)));
-    } else {
-        o = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * lds + (k0 - c2)));
+    const int i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
+    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3)), 1e-8f));
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 1)), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 2)), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    const float *kb = known + (size_t)scene * m * ldk;
+    const float *ka = kb + (size_t)i0 * ldk, *kbb = kb + (size_t)i1 * ldk, *kc = kb + (size_t)i2 * ldk;
+    float *orow = out + (size_t)row * ldo;
+    for (int ch = map.chunk0; ch < chunks; ch += map.step) {
+        const int k0 = ch * 4;
+        float4 o;
+        if (k0 < c2) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(ka + k0));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(kbb + k0));
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(kc + k0));
+            o.x = __fmaf_rn(w2, c.x, __fmaf_rn(w0, a.x, __fmul_rn(w1, b.x)));
+            o.y = __fmaf_rn(w2, c.y, __fmaf_rn(w0, a.y, __fmul_rn(w1, b.y)));
+            o.z = __fmaf_rn(w2, c.z, __fmaf_rn(w0, a.z, __fmul_rn(w1, b.z)));
+            o.w = __fmaf_rn(w2, c.w, __fmaf_rn(w0, a.w, __fmul_rn(w1, b.w)));
+        } else {
+            o = __ldg(reinterpret_cast<const float4 *>(skip + (size_t)row * lds + (k0 - c2)));
+        }
+        __stcs(reinterpret_cast<float4 *>(orow + k0), o);
     }
-    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + k0) = o;
 }
 
 // out[(b,i)][col_off + ch] = bilinear(fmap[b,ch], xy[b,i]); one thread per (point, 4 channels)
@@ -330,34 +354,43 @@ __device__ __forceinline__ void pm_taps(float gx, float gy, int h, int w, int al
 
 __global__ void __launch_bounds__(256)
 grid_gather_pm_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, const float *__restrict__ xy, int align_corners,
-                      float *__restrict__ out, int ldo, long long rows_total, int chunks)
+                      float *__restrict__ out, int ldo, long long rows_total, int chunks, int group_shift)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rows_total * chunks) return;
-    const long long row = t / chunks;
-    const int ch0 = (int)(t - row * chunks) * 4;
+    const PmMap map = pm_map(group_shift);
+    if (map.row >= rows_total) return;
+    const long long row = map.row;
     const int scene = (int)(row / n);
     const float2 g = __ldg(reinterpret_cast<const float2 *>(xy + row * 2));
     int o[4];
     float wt[4];
     pm_taps(g.x, g.y, h, w, align_corners, o, wt);
     const size_t plane = (size_t)h * w;
-    float v[4];
+    for (int ch = map.chunk0; ch < chunks; ch += map.step) {
+        const int ch0 = ch * 4;
+        float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int chn = ch0 + j;
-        if (chn < c) {
-            const float *p = fmap + ((size_t)scene * c + chn) * plane;
-            float acc = __fmul_rn(__ldg(p + o[0]), wt[0]);
-            acc = __fmaf_rn(__ldg(p + o[1]), wt[1], acc);
-            acc = __fmaf_rn(__ldg(p + o[2]), wt[2], acc);
-            acc = __fmaf_rn(__ldg(p + o[3]), wt[3], acc);
-            v[j] = acc;
-        } else {
-            v[j] = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            const int chn = ch0 + j;
+            if (chn < c) {
+                const float *p = fmap + ((size_t)scene * c + chn) * plane;
+                float acc = __fmul_rn(__ldg(p + o[0]), wt[0]);
+                acc = __fmaf_rn(__ldg(p + o[1]), wt[1], acc);
+                acc = __fmaf_rn(__ldg(p + o[2]), wt[2], acc);
+                acc = __fmaf_rn(__ldg(p + o[3]), wt[3], acc);
+                v[j] = acc;
+            } else {
+                v[j] = 0.f;
+            }
         }
+        *reinterpret_cast<float4 *>(out + (size_t)row * ldo + ch0) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4 *>(out + (size_t)row * ldo + ch0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+static inline int pm_group_shift(int chunks)
+{
+    int g = 0;
+    while ((1 << g) < chunks && g < 5) ++g;
+    return g;
 }
 
 }  // namespace epnet
@@ -372,9 +405,10 @@ EPNET_API int epnet_group_concat_pm(int b, int c, int n, int m, int nsample, con
     if (rows == 0) return EPNET_OK;
     const int chunks = (c + 3 + 3) / 4;
     const int vec_ok = c > 0 && (ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
-    const long long threads = rows * chunks;
+    const int gs = pm_group_shift(chunks);
+    const long long threads = rows << gs;
     group_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, n, m, nsample, xyz, new_xyz, feats, ldf, idx,
-                                                                                            out, ldo, rows, chunks, vec_ok);
+                                                                                            out, ldo, rows, chunks, vec_ok, gs);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
@@ -388,9 +422,10 @@ EPNET_API int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int
     const long long rows = (long long)b * n;
     if (rows == 0) return EPNET_OK;
     const int chunks = (c1 + c2) / 4;
-    const long long threads = rows * chunks;
+    const int gs = pm_group_shift(chunks);
+    const long long threads = rows << gs;
     three_interpolate_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2, m, n, c1, known, ldk, idx, dist2,
-                                                                                                        skip, lds, out, ldo, rows, chunks);
+                                                                                                        skip, lds, out, ldo, rows, chunks, gs);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
@@ -403,8 +438,99 @@ EPNET_API int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const floa
     const long long rows = (long long)b * n;
     if (rows == 0) return EPNET_OK;
     const int chunks = (c + 3) / 4;
-    const long long threads = rows * chunks;
+    const int gs = pm_group_shift(chunks);
+    const long long threads = rows << gs;
     grid_gather_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out, ldo,
-                                                                                           rows, chunks);
+                                                                                           rows, chunks, gs);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+// =================================================================================================
+// NHWC image-stream helpers (the image stream runs on the tcgen05 implicit-GEMM convolution, whose activations are
+// NHWC = "pixel-major" rows)
+// =================================================================================================
+namespace epnet {
+
+// LI-Fusion gather from an NHWC feature map: out[(b,i)][0..C) = bilinear(fmap[b,:,:,0..C), xy[b,i]).  Each tap is one
+// contiguous C*4-byte run; lane groups walk it in 16-byte chunks (same mapping as the other point-major kernels).
+__global__ void __launch_bounds__(256)
+grid_gather_nhwc_pm_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, int ldc, const float *__restrict__ xy,
+                           int align_corners, float *__restrict__ out, int ldo, long long rows_total, int chunks, int group_shift)
+{
+    const PmMap map = pm_map(group_shift);
+    if (map.row >= rows_total) return;
+    const long long row = map.row;
+    const int scene = (int)(row / n);
+    const float2 g = __ldg(reinterpret_cast<const float2 *>(xy + row * 2));
+    int o[4];
+    float wt[4];
+    pm_taps(g.x, g.y, h, w, align_corners, o, wt);
+    const float *base = fmap + (size_t)scene * h * w * ldc;
+    const float *t0 = base + (size_t)o[0] * ldc, *t1 = base + (size_t)o[1] * ldc, *t2 = base + (size_t)o[2] * ldc, *t3 = base + (size_t)o[3] * ldc;
+    for (int ch = map.chunk0; ch < chunks; ch += map.step) {
+        const int k0 = ch * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(t0 + k0));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(t1 + k0));
+        const float4 cc = __ldg(reinterpret_cast<const float4 *>(t2 + k0));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(t3 + k0));
+        float4 r;
+        r.x = __fmaf_rn(d.x, wt[3], __fmaf_rn(cc.x, wt[2], __fmaf_rn(b.x, wt[1], __fmul_rn(a.x, wt[0]))));
+        r.y = __fmaf_rn(d.y, wt[3], __fmaf_rn(cc.y, wt[2], __fmaf_rn(b.y, wt[1], __fmul_rn(a.y, wt[0]))));
+        r.z = __fmaf_rn(d.z, wt[3], __fmaf_rn(cc.z, wt[2], __fmaf_rn(b.z, wt[1], __fmul_rn(a.z, wt[0]))));
+        r.w = __fmaf_rn(d.w, wt[3], __fmaf_rn(cc.w, wt[2], __fmaf_rn(b.w, wt[1], __fmul_rn(a.w, wt[0]))));
+        *reinterpret_cast<float4 *>(out + (size_t)row * ldo + k0) = r;
+    }
+}
+
+// ConvTranspose2d with kernel == stride (non-overlapping, lib/net/pointnet2_msg.py:163-165) computed as a GEMM leaves
+// y[(b,y,x)][(ky*k + kx)*co + o]; this scatters it to the full-resolution NHWC concat:
+// out[(b, y*k+ky, x*k+kx)][col_off + o].  One thread per (output pixel, 16-byte chunk).
+__global__ void __launch_bounds__(256)
+deconv_shuffle_nhwc_kernel(int h, int w, int k, int co, const float *__restrict__ y, float *__restrict__ out, int ldo, int col_off,
+                           long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int chunks = co >> 2;
+    const int ch = (int)(t % chunks);
+    const long long opix = t / chunks;           // (b, Y, X) over the full-resolution grid
+    const int W = w * k, H = h * k;
+    const int X = (int)(opix % W);
+    const long long rest = opix / W;
+    const int Y = (int)(rest % H);
+    const int b = (int)(rest / H);
+    const int yy = Y / k, ky = Y - yy * k, xx = X / k, kx = X - xx * k;
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(y + (((size_t)b * h + yy) * w + xx) * (size_t)(k * k * co) + (size_t)(ky * k + kx) * co + ch * 4));
+    *reinterpret_cast<float4 *>(out + (size_t)opix * ldo + col_off + ch * 4) = v;
+}
+
+}  // namespace epnet
+
+EPNET_API int epnet_grid_gather_nhwc_pm(int b, int c, int h, int w, int n, const float *fmap, int ldc, const float *xy, int align_corners,
+                                        float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || c <= 0 || (c & 3) || h <= 0 || w <= 0 || n < 0 || !fmap || !xy || !out || ldc < c || (ldc & 3) || ldo < c || (ldo & 3))
+        return EPNET_ERR_BAD_ARG;
+    if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(fmap)) & 15) || (reinterpret_cast<uintptr_t>(xy) & 7)) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * n;
+    if (rows == 0) return EPNET_OK;
+    const int chunks = c / 4;
+    const int gs = pm_group_shift(chunks);
+    const long long threads = rows << gs;
+    grid_gather_nhwc_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, ldc, xy, align_corners, out,
+                                                                                                ldo, rows, chunks, gs);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, const float *y, float *out, int ldo, int col_off, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h <= 0 || w <= 0 || k <= 0 || co <= 0 || (co & 3) || !y || !out || (ldo & 3) || (col_off & 3) || ldo < col_off + co)
+        return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(y)) & 15) return EPNET_ERR_BAD_ARG;
+    const long long total = (long long)b * h * k * w * k * (co / 4);
+    if (total == 0) return EPNET_OK;
+    deconv_shuffle_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, w, k, co, y, out, ldo, col_off, total);
     EPNET_RETURN_LAUNCH_STATUS();
 }

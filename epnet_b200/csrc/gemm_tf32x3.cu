@@ -99,6 +99,10 @@ struct GemmArgs {
     int pool;              // 1, or the number of consecutive rows pooled by max: 2, 4, 8, 16 or 32
     int stages;
     int x_vec_ok;          // x base 16-byte aligned and ldx % 4 == 0
+    // implicit 3x3 convolution (pad 1): x is an NHWC image (B, H, W, Cin), a GEMM row is an output pixel (b, yo, xo),
+    // k = (ky*3 + kx)*Cin + c; Cin is a power of two >= 4, so a 16-byte chunk never straddles two taps.
+    int conv;              // 0: plain rows, 1: conv gather
+    int H, W, cin_shift, stride, Ho, Wo;
 };
 
 __global__ void __launch_bounds__(kGmThreads, 2)
@@ -154,8 +158,40 @@ gemm_tf32x3_kernel(const GemmArgs a)
         const int chunk = tid & 7;          // 16-byte chunk of the 128-byte k-row
         const int rbase = tid >> 3;         // 0..15; rows rbase + 16*i
         // global loads of k-block kb+1 are issued before k-block kb is converted and stored: one block of latency is hidden
+        // conv mode: (b, yo, xo) of this thread's 8 rows, packed; -1 marks rows past the end
+        int pix_base[8], pix_yx[8];
+        if (a.conv) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = row0 + rbase + 16 * i;
+                if (row < a.L) {
+                    const int b = row / (a.Ho * a.Wo);
+                    const int rem = row - b * (a.Ho * a.Wo);
+                    const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
+                    pix_base[i] = b * a.H;                                   // image row base of the scene
+                    pix_yx[i] = ((yo * a.stride - 1) << 16) | ((xo * a.stride - 1) & 0xffff);  // top-left tap, 16-bit signed each
+                } else {
+                    pix_base[i] = -1;
+                    pix_yx[i] = 0;
+                }
+            }
+        }
         auto load_block = [&](int kb, float4 (&v)[8]) {
             const int k0 = kb * kGmBK + chunk * 4;
+            if (a.conv) {
+                const int tap = k0 >> a.cin_shift;            // (ky*3 + kx); >= 9 in the zero padding of the last k-block
+                const int c = k0 & ((1 << a.cin_shift) - 1);
+                const int ky = tap / 3, kx = tap - 3 * ky;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int yi = (pix_yx[i] >> 16) + ky;
+                    const int xi = (int)(short)(pix_yx[i] & 0xffff) + kx;
+                    if (pix_base[i] >= 0 && tap < 9 && yi >= 0 && yi < a.H && xi >= 0 && xi < a.W)
+                        v[i] = __ldg(reinterpret_cast<const float4 *>(a.x + ((((size_t)(pix_base[i] + yi)) * a.W + xi) << a.cin_shift) + c));
+                }
+                return;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = row0 + rbase + 16 * i;
@@ -313,6 +349,27 @@ gemm_tf32x3_kernel(const GemmArgs a)
 
 }  // namespace epnet
 
+namespace epnet {
+static int gemm_launch(GemmArgs &a, cudaStream_t st)
+{
+    a.n_kblocks = (a.K + kGmBK - 1) / kGmBK;
+    const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
+    int stages = (int)((100 * 1024) / stage_bytes);  // <= ~100 KB per CTA: two CTAs per SM overlap each other's epilogue
+    if (stages > kGmMaxStages) stages = kGmMaxStages;
+    if (stages > a.n_kblocks) stages = a.n_kblocks;
+    if (stages < 2 && a.n_kblocks > 1) stages = 2;
+    if (stages < 1) stages = 1;
+    a.stages = stages;
+    const size_t smem = stage_bytes * stages + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int n_tiles = (a.N + a.BN - 1) / a.BN;
+    dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
+    gemm_tf32x3_kernel<<<grid, kGmThreads, smem, st>>>(a);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+}  // namespace epnet
+
 // x (L, ldx) fp32 rows, wpack from pack_weights (N_tiles x n_kblocks x 2 x BN x 32), bias (N) or NULL -> y (L/pool, ldy).
 EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
                                 int pool, float *y, int ldy, void *stream)
@@ -323,24 +380,34 @@ EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, co
     if (pool < 1 || pool > 32 || (32 % pool) != 0 || (L % pool) != 0) return EPNET_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
     if (L == 0) return EPNET_OK;
-    GemmArgs a;
+    GemmArgs a = {};
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
     a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
-    a.n_kblocks = (K + kGmBK - 1) / kGmBK;
     a.relu = relu; a.pool = pool;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
-    const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)BN * 128;
-    int stages = (int)((100 * 1024) / stage_bytes);  // <= ~100 KB per CTA: two CTAs per SM overlap each other's epilogue
-    if (stages > kGmMaxStages) stages = kGmMaxStages;
-    if (stages > a.n_kblocks) stages = a.n_kblocks;
-    if (stages < 2 && a.n_kblocks > 1) stages = 2;
-    if (stages < 1) stages = 1;
-    a.stages = stages;
-    const size_t smem = stage_bytes * stages + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int n_tiles = (N + BN - 1) / BN;
-    dim3 grid((L + kGmBM - 1) / kGmBM, n_tiles);
-    gemm_tf32x3_kernel<<<grid, kGmThreads, smem, (cudaStream_t)stream>>>(a);
-    EPNET_RETURN_LAUNCH_STATUS();
+    return gemm_launch(a, (cudaStream_t)stream);
+}
+
+// 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM on an NHWC image: x (B, H, W, Cin) with Cin a power of two
+// >= 4; wpack packs W reordered to (Cout, ky, kx, Cin) (K = 9*Cin); y (B*Ho*Wo, ldy) = NHWC output, bias/ReLU optional.
+EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                                        const float *bias, int relu, float *y, int ldy, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h <= 0 || w <= 0 || cin < 4 || (cin & (cin - 1)) != 0 || cout <= 0 || (stride != 1 && stride != 2) || !x || !wpack || !y)
+        return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || ldy < cout || h >= 32768 || w >= 32768) return EPNET_ERR_BAD_ARG;
+    if (((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(x)) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
+    a.conv = 1; a.H = h; a.W = w; a.stride = stride;
+    a.Ho = (h + 2 - 3) / stride + 1; a.Wo = (w + 2 - 3) / stride + 1;
+    a.cin_shift = 0;
+    while ((1 << a.cin_shift) < cin) ++a.cin_shift;
+    const long long rows = (long long)b * a.Ho * a.Wo;
+    if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
+    a.L = (int)rows; a.K = 9 * cin; a.N = cout; a.ldx = cin; a.ldy = ldy; a.BN = BN;
+    a.relu = relu; a.pool = 1; a.x_vec_ok = 1;
+    return gemm_launch(a, (cudaStream_t)stream);
 }

@@ -57,3 +57,33 @@ class PackedLinear:
         pc._call("gemm_tf32x3", LIB.epnet_gemm_tf32x3, x2, L, self.K, self.N, x2.data_ptr(), ldx, self.wpack.data_ptr(), self.BN,
                  None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), pool, out.data_ptr(), ldy)
         return out
+
+
+class PackedConv3x3:
+    """3x3 / pad 1 convolution on NHWC activations as an implicit GEMM (csrc/gemm_tf32x3.cu, conv mode).
+    weight (Cout, Cin, 3, 3) [+ bias]; Cin is zero-padded to a power of two >= 4 (the 3-channel input image becomes 4)."""
+
+    def __init__(self, weight, bias=None, stride=1):
+        w = weight.detach().float()
+        cout, cin = w.shape[:2]
+        cin_p = 4
+        while cin_p < cin:
+            cin_p *= 2
+        wp = torch.zeros(cout, 3, 3, cin_p, device=w.device)
+        wp[..., :cin] = w.permute(0, 2, 3, 1)
+        self.lin = PackedLinear(wp.reshape(cout, 9 * cin_p), bias)
+        self.cin, self.cin_p, self.cout, self.stride = cin, cin_p, cout, stride
+
+    def __call__(self, x, relu=False, out=None):
+        """x (B, H, W, cin_p) NHWC contiguous -> (B, Ho, Wo, Cout)"""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin_p
+        B, H, W, _ = x.shape
+        Ho, Wo = (H - 1) // self.stride + 1, (W - 1) // self.stride + 1
+        if out is None:
+            out = torch.empty((B, Ho, Wo, self.cout), dtype=torch.float32, device=x.device)
+        assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
+        lin = self.lin
+        pc._call("conv3x3_nhwc_tf32x3", LIB.epnet_conv3x3_nhwc_tf32x3, x, B, H, W, self.cin_p, self.cout, self.stride, x.data_ptr(),
+                 lin.wpack.data_ptr(), lin.BN, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(),
+                 out.stride(-2))
+        return out

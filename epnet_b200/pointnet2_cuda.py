@@ -175,3 +175,13 @@ def three_interpolate_concat_pm_wrapper(b, c2, m, n, c1, known_pm, idx, dist2, s
 def grid_gather_pm_wrapper(b, c, h, w, n, fmap, xy, align_corners, out):
     _call("grid_gather_pm", LIB.epnet_grid_gather_pm, fmap, b, c, h, w, n, _f(fmap, "feature_map"), _f(xy, "xy"),
           int(bool(align_corners)), out.data_ptr(), out.stride(0))
+
+
+def grid_gather_nhwc_pm_wrapper(b, c, h, w, n, fmap_nhwc, xy, align_corners, out):
+    """fmap_nhwc (B,H,W,C') with C' >= c channels-last contiguous; out (B*n, ldo)"""
+    _call("grid_gather_nhwc_pm", LIB.epnet_grid_gather_nhwc_pm, fmap_nhwc, b, c, h, w, n, _f(fmap_nhwc, "feature_map"),
+          fmap_nhwc.stride(-2), _f(xy, "xy"), int(bool(align_corners)), out.data_ptr(), out.stride(0))
+
+
+def deconv_shuffle_nhwc_wrapper(b, h, w, k, co, y, out, col_off):
+    _call("deconv_shuffle_nhwc", LIB.epnet_deconv_shuffle_nhwc, y, b, h, w, k, co, _f(y, "y"), out.data_ptr(), out.stride(-2), col_off)

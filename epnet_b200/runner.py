@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
-from .gemm import PackedLinear
+from .gemm import PackedConv3x3, PackedLinear
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -202,7 +202,45 @@ class BackboneRunner:
 
         # ---- image stream ----
         imgs, img_done, img_fusion, img_fusion_done = [], [], None, None
-        if c.li_fusion:
+        if c.li_fusion and pm:
+            # NHWC activations; 3x3 convolutions, transposed convolutions and the 1x1 fusion conv on the tcgen05 3xTF32 GEMM
+            with torch.cuda.stream(self.s_img):
+                self.s_img.wait_event(ready)
+                H, W = self.image.shape[2], self.image.shape[3]
+                x = torch.zeros((B, H, W, 4), **f32)
+                x[..., :3] = self.image.permute(0, 2, 3, 1)
+                def run_conv(conv, inp, relu):
+                    # the next convolution wants a power-of-two channel count: pad the buffer (zeros) when Cout is not one
+                    cp = 4
+                    while cp < conv.cout:
+                        cp *= 2
+                    if cp == conv.cout:
+                        return conv(inp, relu=relu)
+                    ho, wo = (inp.shape[1] - 1) // conv.stride + 1, (inp.shape[2] - 1) // conv.stride + 1
+                    buf = torch.zeros((B, ho, wo, cp), **f32)
+                    conv(inp, relu=relu, out=buf[..., :conv.cout])
+                    return buf
+
+                img_channels = []
+                for conv1, conv2 in self.img_blocks_pm:
+                    x = run_conv(conv2, run_conv(conv1, x, True), False)
+                    ev = torch.cuda.Event()
+                    ev.record(self.s_img)
+                    imgs.append(x)
+                    img_channels.append(conv2.cout)
+                    img_done.append(ev)
+                self._img_channels = img_channels
+                cat = torch.empty((B, H, W, self.deconv_cat_width), **f32)
+                col = 0
+                for i, (lin, k, co) in enumerate(self.deconv_pm):
+                    hi, wi, ci = imgs[i].shape[1], imgs[i].shape[2], img_channels[i]
+                    y = lin(imgs[i].view(-1, imgs[i].shape[3])[:, :ci], relu=False)  # (B*hi*wi, k*k*co): each input pixel's k x k patch
+                    pc.deconv_shuffle_nhwc_wrapper(B, hi, wi, k, co, y, cat, col)
+                    col += co
+                img_fusion = self.img_fuse_pm(cat.view(-1, self.deconv_cat_width), relu=True).view(B, H, W, -1)
+                img_fusion_done = torch.cuda.Event()
+                img_fusion_done.record(self.s_img)
+        elif c.li_fusion:
             with torch.cuda.stream(self.s_img):
                 self.s_img.wait_event(ready)
                 x = self.image
@@ -291,6 +329,22 @@ class BackboneRunner:
         if self.cfg.li_fusion:
             self.fusion_pm = [_FusionPM(m) for m in self.model.Fusion_Conv]
             self.final_fusion_pm = _FusionPM(self.model.final_fusion_img_point)
+            # image stream on the tcgen05 GEMM, NHWC
+            self.img_blocks_pm = [(PackedConv3x3(w1, b1, stride=stride[0]), PackedConv3x3(conv2.weight, None, stride=conv2.stride[0]))
+                                  for (w1, b1, stride, conv2) in self.img_blocks]
+            self.deconv_pm, biases = [], []
+            for de in self.model.DeConv:  # ConvTranspose2d weight: (Cin, Cout, k, k), kernel == stride
+                k, co = de.kernel_size[0], de.out_channels
+                assert de.stride[0] == k and de.kernel_size[1] == k
+                wd = de.weight.detach().permute(2, 3, 1, 0).reshape(k * k * co, de.in_channels)  # row (ky, kx, o)
+                self.deconv_pm.append((PackedLinear(wd, None), k, co))
+                biases.append(de.bias.detach() if de.bias is not None else torch.zeros(co, device=wd.device))
+            self.deconv_cat_width = sum(co for _, _, co in self.deconv_pm)
+            fc, fbn = self.model.image_fusion_conv, self.model.image_fusion_bn
+            wq = fc.weight.detach().flatten(1)
+            # the transposed convolutions' biases pass linearly through the 1x1 fusion conv: fold them into its bias
+            bq = (fc.bias.detach() if fc.bias is not None else 0) + wq @ torch.cat(biases)
+            self.img_fuse_pm = PackedLinear(*_fold_bn(wq, bq, fbn))
 
     def _point_stream_pm(self, main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn):
         c, B, N, dev = self.cfg, self.B, self.N, self.device
@@ -317,11 +371,11 @@ class BackboneRunner:
                 c_off += lins[-1].N
             if c.li_fusion:
                 main.wait_event(img_done[k])
-                img = imgs[k]
-                ci = img.shape[1]
-                g = torch.empty((B * npoint, (ci + 3) // 4 * 4), **f32)
-                pc.grid_gather_pm_wrapper(B, ci, img.shape[2], img.shape[3], npoint, img, l_xy[k + 1], c.align_corners, g)
-                l_feat.append(self.fusion_pm[k](cat, g[:, :ci]))
+                img = imgs[k]  # NHWC, possibly channel-padded
+                ci = self._img_channels[k]
+                g = torch.empty((B * npoint, ci), **f32)
+                pc.grid_gather_nhwc_pm_wrapper(B, ci, img.shape[1], img.shape[2], npoint, img, l_xy[k + 1], c.align_corners, g)
+                l_feat.append(self.fusion_pm[k](cat, g))
             else:
                 l_feat.append(cat)
 
@@ -348,10 +402,10 @@ class BackboneRunner:
         feats = l_feat[0]
         if c.li_fusion:
             main.wait_event(img_fusion_done)
-            ci = img_fusion.shape[1]
-            g = torch.empty((B * N, (ci + 3) // 4 * 4), **f32)
-            pc.grid_gather_pm_wrapper(B, ci, img_fusion.shape[2], img_fusion.shape[3], N, img_fusion, xyn, c.align_corners, g)
-            feats = self.final_fusion_pm(final_cat, g[:, :ci])
+            ci = img_fusion.shape[3]  # NHWC
+            g = torch.empty((B * N, ci), **f32)
+            pc.grid_gather_nhwc_pm_wrapper(B, ci, img_fusion.shape[1], img_fusion.shape[2], N, img_fusion, xyn, c.align_corners, g)
+            feats = self.final_fusion_pm(final_cat, g)
         return feats.view(B, N, -1).transpose(1, 2).contiguous()  # interface layout (B, C, N)
 
     # ------------------------------------------------------------------------------------ graph
@@ -385,8 +439,15 @@ class BackboneRunner:
         self.graph.replay()
         return self.out
 
-    def eager(self, points, image, xy):
-        """Same schedule without the graph (profiling: events around individual launches)."""
+    def eager(self, points, image, xy, single_stream=False):
+        """Same schedule without the graph (profiling: events around individual launches); single_stream=True also
+        serialises the three branches on the current stream so that per-kernel durations are not inflated by overlap."""
         self._load(points, image, xy)
-        with torch.no_grad():
-            return self._forward()
+        saved = (self.s_fps, self.s_img)
+        if single_stream:
+            self.s_fps = self.s_img = torch.cuda.current_stream(self.device)
+        try:
+            with torch.no_grad():
+                return self._forward()
+        finally:
+            self.s_fps, self.s_img = saved

@@ -127,6 +127,20 @@ int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int c1, const
 int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, int ldo,
                          void *stream);
 
+/* 3x3 convolution (padding 1, stride 1 or 2) as an implicit tcgen05 3xTF32 GEMM on an NHWC image -- the image-stream
+ * convolutions of BasicBlock (lib/net/pointnet2_msg.py:17-33; cuDNN fp32 there).  x (B,H,W,Cin), Cin a power of two >= 4;
+ * wpack = the weight reordered to (Cout, ky, kx, Cin) and packed like epnet_gemm_tf32x3's; y (B*Ho*Wo, ldy) NHWC. */
+int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                              const float *bias, int relu, float *y, int ldy, void *stream);
+
+/* NHWC image-stream helpers.  grid_gather_nhwc_pm: Feature_Gather (lib/net/pointnet2_msg.py:107-120) from an NHWC map
+ * (B,H,W,ldc) -> out[(b,i)][0..C).  deconv_shuffle_nhwc: the pixel shuffle of a ConvTranspose2d with kernel == stride
+ * (pointnet2_msg.py:163-165,239-241) computed as a GEMM y (B*h*w, k*k*co) -> out (B, h*k, w*k, ldo)[..., col_off:col_off+co],
+ * i.e. straight into the channel concat of :242. */
+int epnet_grid_gather_nhwc_pm(int b, int c, int h, int w, int n, const float *fmap, int ldc, const float *xy, int align_corners,
+                              float *out, int ldo, void *stream);
+int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, const float *y, float *out, int ldo, int col_off, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,63 @@
+"""Launches each product kernel a few times at a profiling-friendly size (used under ncu: one --set full capture covers
+the whole library).  Shapes: sweep sizes for the memory-bound ops, backbone SA1 sizes for the search kernels."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from epnet_b200 import pointnet2_cuda as pc  # noqa: E402
+from epnet_b200 import scenes  # noqa: E402
+from epnet_b200.gemm import PackedLinear  # noqa: E402
+
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+B = 2
+pts = torch.stack([scenes.lidar_scene(1000 + i) for i in range(B)]).to(dev)
+for _ in range(reps):
+    # --- search kernels at SA1 size
+    temp = torch.full((B, 16384), 1e10, device=dev)
+    idx = torch.empty(B, 4096, dtype=torch.int32, device=dev)
+    new_xyz = torch.empty(B, 4096, 3, device=dev)
+    pc.fps_sample_wrapper(B, 16384, 4096, pts, temp, idx, new_xyz)
+    for r, ns in ((0.1, 16), (0.5, 32)):
+        bidx = torch.zeros(B, 4096, ns, dtype=torch.int32, device=dev)
+        pc.ball_query_wrapper(B, 16384, 4096, r, ns, new_xyz, pts, bidx)
+    d2 = torch.empty(B, 16384, 3, device=dev)
+    i3 = torch.empty(B, 16384, 3, dtype=torch.int32, device=dev)
+    pc.three_nn_wrapper(B, 16384, 4096, pts, new_xyz, d2, i3)
+    # --- memory-bound ops at sweep size (outputs > L2)
+    C, N, M, ns = 128, 65536, 16384, 32
+    xyz = torch.randn(1, N, 3, device=dev)
+    cen = xyz[:, :M].contiguous()
+    feats_cm = torch.randn(1, C, N, device=dev)
+    feats_pm = feats_cm.transpose(1, 2).contiguous()
+    gi = torch.randint(0, N, (1, M, ns), generator=g).int().to(dev)
+    out_cm = torch.empty(1, C, M, ns, device=dev)
+    pc.group_points_wrapper(1, C, N, M, ns, feats_cm, gi, out_cm)
+    out_pm = torch.empty(M * ns, 132, device=dev)
+    pc.group_concat_pm_wrapper(1, C, N, M, ns, xyz, cen, feats_pm, gi, out_pm)
+    C2, m, n = 256, 32768, 131072
+    known_pm = torch.randn(1, m, C2, device=dev)
+    idx3 = torch.randint(0, m, (1, n, 3), generator=g).int().to(dev)
+    dd = torch.rand(1, n, 3, generator=g).to(dev)
+    o = torch.empty(n, C2, device=dev)
+    pc.three_interpolate_concat_pm_wrapper(1, C2, m, n, 0, known_pm, idx3, dd, None, o)
+    w = torch.rand(1, n, 3, generator=g).to(dev)
+    o_cm = torch.empty(1, C2, n, device=dev)
+    pc.three_interpolate_wrapper(1, C2, m, n, known_pm.transpose(1, 2).contiguous(), idx3, w, o_cm)
+    fmap = torch.randn(1, 128, 384, 1280, device=dev)
+    xy = (torch.rand(1, n, 2, generator=g) * 2 - 1).to(dev)
+    og = torch.empty(1, 128, n, device=dev)
+    pc.grid_gather_bilinear_wrapper(1, 128, 384, 1280, n, fmap, xy, False, og)
+    x = torch.randn(2, 64, 491520, device=dev)
+    pc.bias_relu_wrapper(2, 64, 491520, x, torch.randn(64, device=dev))
+    # --- tcgen05 GEMM at a large shared-MLP shape and with the pooled epilogue
+    X = torch.randn(65536, 512, device=dev)
+    lin = PackedLinear(torch.randn(256, 512, device=dev) / 22.6, torch.zeros(256, device=dev))
+    lin(X, relu=True)
+    lin2 = PackedLinear(torch.randn(128, 96, device=dev) / 9.8, torch.zeros(128, device=dev))
+    lin2(X[:, :96], relu=True, pool=32)
+torch.cuda.synchronize()
+print("zoo ok")
