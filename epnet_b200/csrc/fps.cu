@@ -337,23 +337,30 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
 #pragma unroll
         for (int b = 0; b < kBuckets; ++b) {
             if (mask & (1u << b)) {  // warp-uniform
-                float bt = 0.f;
-                uint32_t bk = 0xffffffffu;
+                // lane-local best of the bucket as a tournament (depth log2(kSlots)), ties to the smaller tie word
+                float bt[kSlots];
+                uint32_t bk[kSlots];
 #pragma unroll
                 for (int i = 0; i < kSlots; ++i) {
                     const int pos = FPS_POS(b, i);
-                    const float d = sqdist_ref(xs[pos], ys[pos], zs[pos], cx, cy, cz);
-                    const float v = fminf(d, t[b][i]);
-                    t[b][i] = v;
-                    const bool take = (i == 0) || (v > bt) || (v == bt && tw[b][i] < bk);
-                    bt = take ? v : bt;
-                    bk = take ? tw[b][i] : bk;
+                    bt[i] = fminf(sqdist_ref(xs[pos], ys[pos], zs[pos], cx, cy, cz), t[b][i]);
+                    t[b][i] = bt[i];
+                    bk[i] = tw[b][i];
                 }
-                uint32_t bits = __float_as_uint(bt);
-                warp_argmax(bits, bk);
+#pragma unroll
+                for (int w = 1; w < kSlots; w <<= 1) {
+#pragma unroll
+                    for (int i = 0; i + w < kSlots; i += 2 * w) {
+                        const bool take = (bt[i + w] > bt[i]) || (bt[i + w] == bt[i] && bk[i + w] < bk[i]);
+                        bt[i] = take ? bt[i + w] : bt[i];
+                        bk[i] = take ? bk[i + w] : bk[i];
+                    }
+                }
+                uint32_t bits = __float_as_uint(bt[0]), key = bk[0];
+                warp_argmax(bits, key);
                 if (lane == b) {
                     bmax = bits;
-                    bkey = bk;
+                    bkey = key;
                 }
             }
         }
