@@ -179,18 +179,45 @@ def measure(model, runner, dev_pool, device, world):
     ranked = sorted(agg.items(), key=lambda kv: -kv[1][0])
     kernels = [{"kernel": k[0], "args": list(k[1]), "launches_per_step": v[1] // reps, "us_per_launch": round(v[0] / v[1] * 1e6, 2),
                 "share_of_single_stream_step": round(v[0] / reps / (step_ms * 1e-3), 4)} for k, v in ranked[:12]]
-    (top_name, top_ints), (top_t, top_cnt) = ranked[0]
-    per_launch = top_t / top_cnt
-    by = algorithmic_bytes(top_name, top_ints)
-    out = {
-        "roofline": {"bound": "hbm", "kernel": top_name, "args": list(top_ints), "achieved": round(by / per_launch / 1e9, 3),
-                     "peak": peak, "unit": "GB/s", "frac": round(by / per_launch / 1e9 / peak, 5), "traffic": None,
-                     "peak_source": peak_src, "us_per_launch": round(per_launch * 1e6, 2), "algorithmic_bytes": by,
-                     "note": "dominant product kernel of the step by device time (CUDA events around each launch of an eager, single-stream "
-                             "pass of the same schedule).  FPS is a serial, latency-bound kernel: its meaningful figure is fps_ns_per_iteration"},
-        "kernel_breakdown": kernels,
-        "eager_single_stream_step_ms": round(step_ms, 3),
-    }
+    # per kernel NAME: total time, algorithmic bytes / flops over all its launches of one step
+    by_name = {}
+    for (name, ints), (tot, cnt) in agg.items():
+        e = by_name.setdefault(name, {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
+        e["time"] += tot / reps
+        e["launches"] += cnt // reps
+        e["bytes"] += algorithmic_bytes(name, ints) * (cnt // reps)
+        if name == "gemm_tf32x3":
+            e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
+        if name == "conv3x3_nhwc_tf32x3":  # (b, h, w, cin, cout, stride, BN, relu, ldy)
+            b_, h_, w_, ci_, co_, st_ = ints[:6]
+            ho, wo = (h_ - 1) // st_ + 1, (w_ - 1) // st_ + 1
+            e["flops"] += 2.0 * b_ * ho * wo * 9 * ci_ * co_ * (cnt // reps)
+            e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * 9 * ci_ * co_ + b_ * ho * wo * co_) * (cnt // reps)
+    bf16_peak = 1383.2
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16_peak = float(json.load(f).get("bf16_tflops_sustained", bf16_peak))
+    except Exception:  # noqa: BLE001
+        pass
+    per_kernel = []
+    for name, e in sorted(by_name.items(), key=lambda kv: -kv[1]["time"]):
+        row = {"kernel": name, "launches_per_step": e["launches"], "us_per_step": round(e["time"] * 1e6, 1),
+               "share_of_single_stream_step": round(e["time"] / (step_ms * 1e-3), 4)}
+        if e["flops"] > 0:  # tcgen05 3xTF32: the tensor pipe executes 3 TF32 MMAs per fp32-equivalent product
+            row.update({"bound": "tensor", "achieved": round(3 * e["flops"] / e["time"] / 1e12, 1), "peak": round(bf16_peak / 2, 1),
+                        "unit": "TFLOP/s", "frac": round(3 * e["flops"] / e["time"] / 1e12 / (bf16_peak / 2), 4),
+                        "fp32_equiv_tflops": round(e["flops"] / e["time"] / 1e12, 1)})
+        else:
+            row.update({"bound": "hbm", "achieved": round(e["bytes"] / e["time"] / 1e9, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(e["bytes"] / e["time"] / 1e9 / peak, 5)})
+        per_kernel.append(row)
+    top = dict(per_kernel[0])
+    top.update({"traffic": None, "peak_source": peak_src if top["bound"] == "hbm" else
+                "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense TF32 runs at half the bf16 rate; no TF32 figure is measured)",
+                "algorithmic": "sum over the kernel's launches in one step of SURVEY.md 8(d) bytes, or 3 x 2*L*K*N TF32 flops",
+                "note": "dominant product kernel of the step by total device time (CUDA events around each launch of an eager, "
+                        "single-stream pass of the same schedule)"})
+    out = {"roofline": top, "rooflines_by_kernel": per_kernel, "kernel_breakdown": kernels, "eager_single_stream_step_ms": round(step_ms, 3)}
     fps = [(k, v) for k, v in agg.items() if k[0] in ("furthest_point_sampling", "fps_sample")]
     if fps:
         out["fps_ns_per_iteration"] = {"%d->%d" % (k[1][1], k[1][2]): round(v[0] / v[1] / max(k[1][2] - 1, 1) * 1e9, 1) for k, v in fps}
