@@ -177,12 +177,14 @@ class Pointnet2MSG(nn.Module):
             self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k]),
                                                     ops=self._ops))
 
-    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm"):
+    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", pipeline=1):
         """Inference fast path (eval mode): one CUDA graph with the FPS chain, the image stream and the point
         stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py."""
         if self.reference_composition:
             raise RuntimeError("reference_composition=True pins the op-by-op path")
-        from .runner import BackboneRunner
+        from .runner import BackboneRunner, PipelinedRunner
+        if pipeline > 1:
+            return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, layout=layout)
         return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, layout=layout)
 
     @staticmethod

@@ -451,3 +451,37 @@ class BackboneRunner:
                 return self._forward()
         finally:
             self.s_fps, self.s_img = saved
+
+
+class PipelinedRunner:
+    """`depth` BackboneRunners (own static buffers, own captured graph, shared weights) replayed round-robin on their own
+    streams, so that successive batches overlap on the GPU.  One forward is latency-bound -- its critical path is the serial
+    FPS chain, which occupies one SM per scene -- so a single batch leaves most of the 148 SMs idle most of the time; a
+    serving loop that keeps 2-3 batches in flight fills them.  Results of call i stay valid until call i + depth."""
+
+    def __init__(self, model, batch, npoints, device, depth=2, **kw):
+        self.device = device
+        self.runners = [BackboneRunner(model, batch, npoints, device, **kw) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
+        self.kernel_launches_per_replay = self.runners[0].kernel_launches_per_replay
+        self.calls = 0
+
+    def __call__(self, points, image, xy):
+        i = self.calls % len(self.runners)
+        self.calls += 1
+        st = self.streams[i]
+        st.wait_stream(torch.cuda.current_stream(self.device))  # inputs produced on the caller's stream
+        with torch.cuda.stream(st):
+            return self.runners[i](points, image, xy)
+
+    def stream_of_last_call(self):
+        return self.streams[(self.calls - 1) % len(self.runners)]
+
+    def join(self):
+        """make the caller's current stream wait for every in-flight batch"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def eager(self, *a, **kw):
+        return self.runners[0].eager(*a, **kw)
