@@ -46,7 +46,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -147,7 +147,7 @@ def cpu_baseline_leg(sample_scenes=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 in cuDNN/cuBLAS (default 0: strict fp32 in both arms)")
@@ -155,6 +155,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="ours: run eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--pipeline", type=int, default=3, help="ours: batches kept in flight (PipelinedRunner depth; 1 = one at a time)")
     ap.add_argument("--layout", choices=["pm", "cm"], default="pm")
+    ap.add_argument("--mode", choices=["infer", "train"], default="infer",
+                    help="train = BASELINE.json configs[2]: forward+backward+Adam through the module path, train-mode BN, DDP gradient "
+                         "all-reduce over NCCL when launched under torchrun (batch 2 per GPU)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,12 +185,28 @@ def main():
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_pool[:4]]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
 
-    use_graph = args.impl == "ours" and not args.no_graph
+    use_graph = args.impl == "ours" and not args.no_graph and args.mode == "infer"
     runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device, layout=args.layout, pipeline=args.pipeline) if use_graph else None
     depth = args.pipeline if runner is not None else 1
 
+    train_model = opt = None
+    if args.mode == "train":
+        model.train()
+        train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if distributed else model
+        opt = torch.optim.Adam(train_model.parameters(), lr=1e-4)
+
+    def train_step(points, image, xy):
+        opt.zero_grad(set_to_none=True)
+        _, feats = train_model(points, image, xy)
+        loss = (feats * feats).mean()
+        loss.backward()  # DDP all-reduces the gradients (NCCL) overlapped with the backward
+        opt.step()
+        return loss
+
     def step_resident(i):
         b = dev_pool[i % POOL]
+        if args.mode == "train":
+            return train_step(b["points"], b["image"], b["xy"].clone())
         with torch.no_grad():
             if runner is not None:
                 return runner(b["points"], b["image"], b["xy"])
@@ -209,6 +228,13 @@ def main():
             pts = hb["points"].to(device, non_blocking=True)
             img = hb["image"].to(device, non_blocking=True)
             xy = hb["xy"].to(device, non_blocking=True)
+            if args.mode == "train":  # result read back = the loss
+                loss = train_step(pts, img, xy)
+                if out_host[slot] is None:
+                    out_host[slot] = (torch.empty((), dtype=torch.float32).pin_memory(),)
+                out_host[slot][0].copy_(loss.detach(), non_blocking=True)
+                st.synchronize()
+                return
             with torch.no_grad():
                 xyz, feats = runner(pts, img, xy) if runner is not None else model(pts, img, xy)
         if out_host[slot] is None:
@@ -249,7 +275,8 @@ def main():
 
     scenes_total = BATCH_PER_GPU * world * args.steps
     line = {
-        "metric": "RPN backbone scenes/s (forward, 16384 pts + 384x1280 image, LI-Fusion with attention)",
+        "metric": "RPN backbone scenes/s (forward, 16384 pts + 384x1280 image, LI-Fusion with attention)" if args.mode == "infer" else
+                  "RPN backbone training scenes/s (forward+backward+Adam, train-mode BN, DDP all-reduce, 16384 pts + 384x1280 image)",
         "value": round(scenes_total / (ms / 1e3), 3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -273,7 +300,7 @@ def main():
                                           "for sm_100a into oracle/_ref) under the reference's op-by-op module composition and ATen "
                                           "grid_sample, same B200, same inputs/weights/precision -- BASELINE.json's second baseline"}
 
-    if rank == 0 and args.impl == "ours":
+    if rank == 0 and args.impl == "ours" and args.mode == "infer":
         try:
             import bench_roofline
             line.update(bench_roofline.measure(model, runner, dev_pool, device, world))
