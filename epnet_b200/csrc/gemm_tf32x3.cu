@@ -363,7 +363,10 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
     const size_t smem = stage_bytes * stages + 1024;
     // the opt-in limit is a property of the function, not of a launch: always raise it to the hardware maximum so that a
     // kernel node captured in a CUDA graph with a large request stays launchable after later, smaller launches
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tf32x3_kernel);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = (a.N + a.BN - 1) / a.BN;
     dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
