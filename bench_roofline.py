@@ -182,7 +182,9 @@ def measure(model, runner, dev_pool, device, world):
     # per kernel NAME: total time, algorithmic bytes / flops over all its launches of one step
     by_name = {}
     for (name, ints), (tot, cnt) in agg.items():
-        e = by_name.setdefault(name, {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
+        # the implicit-GEMM convolution is the same device kernel as the GEMM (conv mode of gemm_tf32x3_kernel)
+        e = by_name.setdefault("gemm_tf32x3_kernel" if name in ("gemm_tf32x3", "conv3x3_nhwc_tf32x3") else name,
+                               {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
         e["time"] += tot / reps
         e["launches"] += cnt // reps
         e["bytes"] += algorithmic_bytes(name, ints) * (cnt // reps)
@@ -212,7 +214,15 @@ def measure(model, runner, dev_pool, device, world):
                         "frac": round(e["bytes"] / e["time"] / 1e9 / peak, 5)})
         per_kernel.append(row)
     top = dict(per_kernel[0])
-    top.update({"traffic": None, "peak_source": peak_src if top["bound"] == "hbm" else
+    traffic = None
+    try:  # DRAM bytes of one representative launch from the committed ncu capture (profiles/r01_ncu_traffic.json)
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            t = json.load(f).get({"gemm_tf32x3_kernel": "gemm_tf32x3", "fps_sample": "fps_bucket_kernel<16,8,4>"}.get(top["kernel"], top["kernel"]))
+        if t:
+            traffic = {"bytes": t["dram_read"] + t["dram_write"], "algorithmic_bytes_same_launch": t["algorithmic_bytes"], "shape": t["shape"]}
+    except Exception:  # noqa: BLE001
+        pass
+    top.update({"traffic": traffic, "peak_source": peak_src if top["bound"] == "hbm" else
                 "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense TF32 runs at half the bf16 rate; no TF32 figure is measured)",
                 "algorithmic": "sum over the kernel's launches in one step of SURVEY.md 8(d) bytes, or 3 x 2*L*K*N TF32 flops",
                 "note": "dominant product kernel of the step by total device time (CUDA events around each launch of an eager, "
