@@ -23,7 +23,8 @@
 // Sorted coordinates live in shared memory as three planes (192 KB at N = 16384), running distances and
 // tie words in registers (lane l of warp w owns sorted positions (((b*NW+w)*kSlots+i)*32+l), bucket boxes and
 // cached winners in the registers of lanes 0..7.  One __syncthreads per iteration (none when a single
-// warp holds the whole cloud, N <= 1024).  N > 16384 streams from L2 (fps_streaming_kernel).
+// warp holds the whole cloud, N <= 256).  16384 < N <= 131072 spreads a scene over a thread-block cluster (DSMEM exchange of
+// the per-CTA winners); beyond that coordinates stream from L2 (fps_streaming_kernel).
 #include <cstdlib>
 #include "common.cuh"
 
@@ -35,6 +36,12 @@ constexpr float kBoxDeflate = 0.999996f;  // > (1 - 2^-18): covers the few-ulp r
 struct FpsCand {
     uint32_t dist_bits;
     uint32_t tie;
+};
+struct FpsClusterCand {  // 32 bytes: one v4 + one scalar remote store
+    uint32_t bits, key;
+    float x, y;
+    float z;
+    uint32_t pad[3];
 };
 
 // ---- tie words -------------------------------------------------------------------------------
@@ -77,16 +84,23 @@ __device__ __forceinline__ void warp_argmax(uint32_t &bits, uint32_t &tie)
 // NW warps, kBuckets buckets per warp (lane b keeps bucket b's box), kSlots points per lane per bucket (bucket = 32*kSlots sorted points).
 // Buckets are dealt to warps round-robin (bucket g -> warp g % NW): buckets that are neighbours in Morton
 // order, i.e. the ones a new sample touches together, are updated by different warps in parallel.
-template <int NW, int kBuckets, int kSlots>
+// kCluster: one scene is spread over a thread-block cluster of `csize` CTAs (N up to 8 x 16384): CTA r owns the original
+// indices [r*slice, (r+1)*slice), sorts and buckets them on its own, and after the CTA-level arg-max the csize candidates
+// (distance bits, tie word, coordinates) are exchanged through distributed shared memory -- every CTA stores its candidate
+// into every peer's slot array (st.shared::cluster), one barrier.cluster per iteration, every warp re-reduces locally.
+template <int NW, int kBuckets, int kSlots, bool kCluster>
 __global__ void __launch_bounds__(NW * 32, 1)
-fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
-                  float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
+fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
+                  float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim, int csize,
+                  int slice)
 {
     constexpr int T = NW * 32;
     constexpr int CAP = T * kBuckets * kSlots;  // sorted positions this CTA can hold
     constexpr int PPT = CAP / T;                // points per thread during the sort
     constexpr int NCELL = CAP;                  // one cell per sorted position on average; the histogram aliases one plane
     constexpr int CB = CAP == 256 ? 8 : CAP == 1024 ? 10 : CAP == 4096 ? 12 : 14;
+    constexpr int PB = kCluster ? 14 : 16;  // position bits of a tie word (cluster: ck needs up to 17 bits)
+    constexpr uint32_t PMASK = (1u << PB) - 1u;
     static_assert((1 << CB) == NCELL, "cell bits");
     static_assert(kBuckets <= 32, "one lane per bucket");
 #define FPS_POS(b, i) ((((b) * NW + warp) * kSlots + (i)) * 32 + lane)
@@ -105,29 +119,35 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     __shared__ int bit_axis[16];      // axis providing Morton bit s (MSB first)
     __shared__ uint32_t warp_tot[32];
     __shared__ FpsCand slots[2][32];
+    __shared__ __align__(16) FpsClusterCand cslots[2][8];
 
-    const int scene = blockIdx.x;
-    xyz += (size_t)scene * n * 3;
-    temp += (size_t)scene * n;
+    const int scene = kCluster ? blockIdx.x / csize : blockIdx.x;
+    const int rank = kCluster ? blockIdx.x % csize : 0;   // == %cluster_ctarank for a 1-D cluster
+    const int first = rank * slice;                        // first original index owned by this CTA
+    const int n = kCluster ? min(slice, n_total - first) : n_total;  // points owned by this CTA
+    const float *xyz_scene = xyz + (size_t)scene * n_total * 3;
+    xyz = xyz_scene + (size_t)first * 3;
+    float *temp_scene = temp + (size_t)scene * n_total;
+    temp = temp_scene + first;
     idx += (size_t)scene * m;
     if (new_xyz) new_xyz += (size_t)scene * m * 3;
     if (aux_out) {
-        aux_in += (size_t)scene * n * aux_dim;
+        aux_in += (size_t)scene * n_total * aux_dim;
         aux_out += (size_t)scene * m * aux_dim;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inf = __int_as_float(0x7f800000);
 
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         idx[0] = 0;
         if (new_xyz) {
-            new_xyz[0] = __ldg(xyz);
-            new_xyz[1] = __ldg(xyz + 1);
-            new_xyz[2] = __ldg(xyz + 2);
+            new_xyz[0] = __ldg(xyz_scene);
+            new_xyz[1] = __ldg(xyz_scene + 1);
+            new_xyz[2] = __ldg(xyz_scene + 2);
         }
     }
     if (m == 1) {
-        if (aux_out && tid < aux_dim) aux_out[tid] = __ldg(aux_in + tid);
+        if (aux_out && rank == 0 && tid < aux_dim) aux_out[tid] = __ldg(aux_in + tid);
         return;
     }
 
@@ -253,7 +273,7 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
         const int k = tid + i * T;
         if (k < n) {
             carry_t[code[i]] = temp[k];
-            carry_k[code[i]] = (uint32_t)k;
+            carry_k[code[i]] = (uint32_t)(first + k);  // ORIGINAL (scene-wide) index: the tie rule is defined on it
         }
     }
     __syncthreads();
@@ -266,7 +286,7 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
             const int pos = FPS_POS(b, i);
             if (pos < n) {
                 t[b][i] = carry_t[pos];
-                tw[b][i] = (fps_compact_key(carry_k[pos], L, qbits) << 16) | (uint32_t)pos;
+                tw[b][i] = (fps_compact_key(carry_k[pos], L, qbits) << PB) | (uint32_t)pos;
             } else {  // empty slot: never changes, loses every tie
                 t[b][i] = 0.f;
                 tw[b][i] = 0xffffffffu;
@@ -323,7 +343,7 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     }
 
     // ---------------- 7. the sampling loop ----------------
-    float cx = __ldg(xyz), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // sample 0 is point 0
+    float cx = __ldg(xyz_scene), cy = __ldg(xyz_scene + 1), cz = __ldg(xyz_scene + 2);  // sample 0 is point 0 of the scene
     uint32_t warp_bits = lane < kBuckets ? bmax : 0u, warp_key = lane < kBuckets ? bkey : 0xffffffffu;
     warp_argmax(warp_bits, warp_key);
     for (int j = 1; j < m; ++j) {
@@ -382,12 +402,36 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
             wkey = lane < NW ? slots[par][lane].tie : 0xffffffffu;
             warp_argmax(wbits, wkey);
         }
-        const uint32_t pos = wkey & 0xffffu;
+        const uint32_t pos = wkey & PMASK;
         cx = xs[pos];
         cy = ys[pos];
         cz = zs[pos];
-        if (tid == 0) {
-            idx[j] = (int)fps_key_to_index(wkey >> 16, L, qbits);
+        if (kCluster) {
+            // publish this CTA's candidate in every CTA of the cluster (lane r of warp 0 writes to rank r), one cluster barrier,
+            // then every warp picks the winner among the csize candidates it finds in its OWN shared memory
+            const int par = j & 1;
+            if (warp == 0 && lane < csize) {
+                const uint32_t local = smem_u32(&cslots[par][rank]);
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(lane));
+                asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"(wbits), "r"(wkey), "r"(__float_as_uint(cx)),
+                             "r"(__float_as_uint(cy))
+                             : "memory");
+                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + 16), "r"(__float_as_uint(cz)) : "memory");
+            }
+            asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            uint32_t gb = lane < csize ? cslots[par][lane].bits : 0u;
+            uint32_t gk = lane < csize ? cslots[par][lane].key : 0xffffffffu;
+            const uint32_t mine = gk;
+            warp_argmax(gb, gk);
+            const int src = __ffs(__ballot_sync(0xffffffffu, mine == gk && lane < csize)) - 1;  // tie words are unique
+            cx = cslots[par][src].x;
+            cy = cslots[par][src].y;
+            cz = cslots[par][src].z;
+            wkey = gk;
+        }
+        if (tid == 0 && rank == 0) {
+            idx[j] = (int)fps_key_to_index(wkey >> PB, L, qbits);
             if (new_xyz) {
                 new_xyz[3 * j] = cx;
                 new_xyz[3 * j + 1] = cy;
@@ -397,7 +441,7 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     }
 
     // per-sample payload (LI-Fusion pixel coordinates) follows the samples: aux_out[j] = aux_in[idx[j]]
-    if (aux_out) {
+    if (aux_out && rank == 0) {
         __syncthreads();  // idx[] written by thread 0 is visible to the CTA
         for (int e = tid; e < m * aux_dim; e += T) {
             const int j = e / aux_dim, a = e - j * aux_dim;
@@ -410,7 +454,7 @@ fps_bucket_kernel(int n, int m, int L, int qbits, const float *__restrict__ xyz,
     for (int b = 0; b < kBuckets; ++b)
 #pragma unroll
         for (int i = 0; i < kSlots; ++i)
-            if (tw[b][i] != 0xffffffffu) temp[fps_key_to_index(tw[b][i] >> 16, L, qbits)] = t[b][i];
+            if (tw[b][i] != 0xffffffffu) temp_scene[fps_key_to_index(tw[b][i] >> PB, L, qbits)] = t[b][i];
 }
 
 // ---- N too large for one SM's shared memory: coordinates and running distances stream from L2 ----
@@ -477,9 +521,38 @@ static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz
                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
 {
     const size_t smem = (size_t)3 * NW * 32 * kBuckets * kSlots * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<NW, kBuckets, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = fps_bucket_kernel<NW, kBuckets, kSlots, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    fps_bucket_kernel<NW, kBuckets, kSlots><<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
+    kernel<<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, 1, n);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+// 16384 < N <= 8 * 16384: a thread-block cluster of ceil(N / 16384) CTAs per scene, each with the full resident layout
+static int launch_cluster(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
+                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
+{
+    constexpr int NW = 16, KB = 8, KS = 4;
+    const int csize = (n + kFpsMaxResident - 1) / kFpsMaxResident;
+    const int slice = (n + csize - 1) / csize;
+    const size_t smem = (size_t)3 * NW * 32 * KB * KS * sizeof(float);
+    auto kernel = fps_bucket_kernel<NW, KB, KS, true>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * csize));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, csize, slice);
+    if (e != cudaSuccess) return (int)e;
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
@@ -511,6 +584,12 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         if (variant == 1) return launch_bucket<8, 16, 4>(EPNET_FPS_ARGS);      // 128 buckets of 128, 8 warps
         return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                        // 128 buckets of 128
 #undef EPNET_FPS_ARGS
+    }
+    if (n <= 8 * kFpsMaxResident) {
+        const int q = (n + 1023) >> 10;
+        int qbits = 0;
+        while ((1 << qbits) < q) ++qbits;
+        return launch_cluster(b, n, m, 10, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st);
     }
     fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
     EPNET_RETURN_LAUNCH_STATUS();

@@ -24,6 +24,10 @@ def ours():
     ("lattice", 2, 300, 150), ("lattice", 2, 1024, 256), ("lattice", 1, 2100, 300), ("identical", 2, 70, 20),
     ("uniform", 2, 1500, 300), ("gauss", 2, 4096, 1024), ("lattice", 1, 5000, 700), ("uniform", 1, 12000, 500),
     ("lattice", 1, 16384, 600), ("gauss", 1, 20000, 300),
+    # 16384 < N <= 131072: thread-block cluster of 2..8 CTAs exchanging candidates through DSMEM
+    ("lattice", 1, 40000, 400), ("uniform", 2, 65536, 300), ("gauss", 1, 131072, 200), ("lattice", 2, 16385, 100),
+    # beyond the cluster's capacity: streaming kernel
+    ("uniform", 1, 140000, 40),
 ])
 def test_fps_bit_exact(ours, kind, b, n, m):
     xyz = cloud(11, b, n, kind, dup_frac=0.05 if n > 100 else 0.0)
