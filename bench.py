@@ -251,13 +251,12 @@ def main():
         if runner is not None and depth > 1:
             runner.join()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few hundred ms to start reporting: it runs through warm-up and the timed region
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     pointnet2_cuda.LAUNCHES[0] = 0
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` sees exactly the timed steps (no-op otherwise)
     ms = timed_region(step_resident, args.steps, rank_sync, drain)
