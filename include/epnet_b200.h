@@ -141,6 +141,15 @@ int epnet_grid_gather_nhwc_pm(int b, int c, int h, int w, int n, const float *fm
                               float *out, int ldo, void *stream);
 int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, const float *y, float *out, int ldo, int col_off, void *stream);
 
+/* ---- next row of the scope table: 3D RoI point pooling ------------------------------------------------------------ */
+
+/* replaces roipool3dLauncher (/root/reference/lib/utils/roipool3d/src/roipool3d.cpp:8-9, roipool3d_kernel.cu:207-236), same
+ * arguments plus the stream.  xyz (B,N,3), boxes3d (B,M,7) [x, bottom y, z, h, w, l, ry], pts_feature (B,N,C) ->
+ * pooled_features (B,M,sampled,3+C) and pooled_empty_flag (B,M), both arriving zeroed (roipool3d_utils.py:20-22);
+ * sampled <= 512.  Unlike the reference it allocates nothing and does not synchronise. */
+int epnet_roipool3d(int b, int n, int m, int c, int sampled, const float *xyz, const float *boxes3d, const float *pts_feature,
+                    float *pooled_features, int *pooled_empty_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ _interp = _sig("oracle_three_interpolate", _i, _i, _i, _i, _F, _I, _F, _F)
 _interp_grad = _sig("oracle_three_interpolate_grad", _i, _i, _i, _i, _F, _I, _F, _F)
 _grid = _sig("oracle_grid_gather_bilinear", _i, _i, _i, _i, _i, _F, _F, _i, _F)
 _grid_grad = _sig("oracle_grid_gather_bilinear_grad", _i, _i, _i, _i, _i, _F, _F, _i, _F)
+_roi = _sig("oracle_roipool3d", _i, _i, _i, _i, _i, _F, _F, _F, _F, _I)
 _lib.oracle_fps_block_size.argtypes = [_i]
 _lib.oracle_fps_block_size.restype = _i
 
@@ -169,6 +170,17 @@ def grid_gather_bilinear_grad(grad_out, xy, h, w, align_corners=False):
     g = np.zeros((B, C, h, w), dtype=np.float32)
     _grid_grad(B, C, h, w, N, grad_out, xy, int(bool(align_corners)), g)
     return g
+
+
+def roipool3d(pts, pts_feature, boxes3d, sampled=512):
+    """boxes3d already enlarged.  -> pooled_features (B,M,sampled,3+C), pooled_empty_flag (B,M)"""
+    pts, pts_feature, boxes3d = _f32(pts), _f32(pts_feature), _f32(boxes3d)
+    B, N, _ = pts.shape
+    M, C = boxes3d.shape[1], pts_feature.shape[2]
+    out = np.zeros((B, M, sampled, 3 + C), dtype=np.float32)
+    flag = np.zeros((B, M), dtype=np.int32)
+    _roi(B, N, M, C, sampled, pts, boxes3d, pts_feature, out, flag)
+    return out, flag
 
 
 def fps_tie_rule_bruteforce(xyz, npoint):

@@ -19,7 +19,9 @@ FLAGS="-O2 -std=c++17 -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -
 for f in sampling_gpu ball_query_gpu group_points_gpu interpolate_gpu; do
     $NVCC $FLAGS -c "$SRC/$f.cu" -o "$OUT/$f.o"
 done
+ROI=${EPNET_REFERENCE_ROI:-/root/reference/lib/utils/roipool3d/src}
+$NVCC $FLAGS -c "$ROI/roipool3d_kernel.cu" -o "$OUT/roipool3d_kernel.o"   # next-row oracle: the reference's RoI pooling kernels, unmodified
 $NVCC $FLAGS -c "$HERE/ref_shim.cu" -o "$OUT/ref_shim.o"
-$NVCC -shared -o "$OUT/libpointnet2_ref.so" "$OUT"/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libpointnet2_ref.so" "$OUT"/*.o -lcudart
 rm -f "$OUT"/*.o
 echo "built $OUT/libpointnet2_ref.so"

@@ -295,3 +295,52 @@ ORACLE_API void oracle_grid_gather_bilinear_grad(int b, int c, int h, int w, int
             }
         }
 }
+
+/* ---- next row: 3D RoI point pooling ------------------------------------------------------------
+ * /root/reference/lib/utils/roipool3d/src/roipool3d_kernel.cu: pt_in_box3d (:14-28), assign_pts_to_box3d (:97-120),
+ * get_pooled_idx (:123-160: first `sampled` inside points in index order, cyclic repetition k % cnt, empty flag) and the copy
+ * (:163-195).  Arithmetic as nvcc -O2 compiles it (PTX-checked): the double-typed literals only widen exactly-representable
+ * halves, so float compares are equivalent; x_rot is two products and a subtraction (no FMA), z_rot one product and one FMA.
+ * cosf/sinf come from the C library here and from libdevice on the GPU: they can differ in the last bit, which can only flip
+ * a point lying within ~1 ulp of a box face; tests compare this oracle with the reference kernel on the same inputs. */
+static int oracle_pt_in_box3d(float x, float y, float z, const float *box)
+{
+    const float cx = box[0], bottom_y = box[1], cz = box[2], h = box[3], w = box[4], l = box[5], angle = box[6];
+    const float half_h = h * 0.5f, half_w = w * 0.5f, half_l = l * 0.5f;
+    const float cy = bottom_y - half_h;
+    const float dx = x - cx, dz = z - cz;
+    if (fabsf(dx) > 10.0f || fabsf(y - cy) > half_h || fabsf(dz) > 10.0f) return 0;
+    const float cosa = cosf(angle), sina = sinf(angle);
+    const float p0 = dx * cosa, p1 = dz * sina;
+    const float x_rot = p0 - p1;
+    const float z_rot = fmaf(dz, cosa, dx * sina);
+    return (x_rot >= -half_l) & (x_rot <= half_l) & (z_rot >= -half_w) & (z_rot <= half_w);
+}
+
+ORACLE_API void oracle_roipool3d(int b, int n, int m, int c, int sampled, const float *xyz, const float *boxes3d, const float *pts_feature,
+                                 float *pooled_features, int *pooled_empty_flag)
+{
+    int *sel = (int *)malloc(sizeof(int) * (size_t)sampled);
+    for (int s = 0; s < b; ++s)
+        for (int j = 0; j < m; ++j) {
+            const float *box = boxes3d + ((size_t)s * m + j) * 7;
+            int cnt = 0;
+            for (int k = 0; k < n && cnt < sampled; ++k) {
+                const float *p = xyz + ((size_t)s * n + k) * 3;
+                if (oracle_pt_in_box3d(p[0], p[1], p[2], box)) sel[cnt++] = k;
+            }
+            if (cnt == 0) {
+                pooled_empty_flag[(size_t)s * m + j] = 1;
+                continue;
+            }
+            for (int k = cnt; k < sampled; ++k) sel[k] = sel[k % cnt];
+            float *out = pooled_features + ((size_t)s * m + j) * sampled * (3 + c);
+            for (int k = 0; k < sampled; ++k) {
+                const float *p = xyz + ((size_t)s * n + sel[k]) * 3;
+                float *o = out + (size_t)k * (3 + c);
+                o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+                if (c > 0) memcpy(o + 3, pts_feature + ((size_t)s * n + sel[k]) * c, sizeof(float) * (size_t)c);
+            }
+        }
+    free(sel);
+}

@@ -36,6 +36,7 @@ def _load():
             "ref_three_nn": [_c_int] * 3 + [_c_void_p] * 5,
             "ref_three_interpolate": [_c_int] * 4 + [_c_void_p] * 5,
             "ref_three_interpolate_grad": [_c_int] * 4 + [_c_void_p] * 5,
+            "ref_roipool3d": [_c_int] * 5 + [_c_void_p] * 5,
         }
         for name, argtypes in sigs.items():
             fn = getattr(lib, name)
@@ -101,3 +102,15 @@ def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tens
 def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
     _load().ref_three_interpolate_grad(b, c, n, m, _p(grad_out_tensor), _p(idx_tensor), _p(weight_tensor),
                                        _p(grad_points_tensor), _s(grad_out_tensor))
+
+
+def roipool3d(pts, boxes3d, pts_feature, sampled=512):
+    """The reference's roipool3dLauncher on already-enlarged boxes (it allocates and frees its own scratch, default stream)."""
+    B, N, _ = pts.shape
+    M, C = boxes3d.shape[1], pts_feature.shape[2]
+    out = torch.zeros((B, M, sampled, 3 + C), dtype=torch.float32, device=pts.device)
+    flag = torch.zeros((B, M), dtype=torch.int32, device=pts.device)
+    torch.cuda.synchronize()
+    _load().ref_roipool3d(B, N, M, C, sampled, _p(pts), _p(boxes3d), _p(pts_feature), _p(out), _p(flag))
+    torch.cuda.synchronize()
+    return out, flag

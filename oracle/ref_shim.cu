@@ -37,3 +37,11 @@ REF_API void ref_three_interpolate(int b, int c, int m, int n, const float *poin
 
 REF_API void ref_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, void *stream)
 { three_interpolate_grad_kernel_launcher_fast(b, c, n, m, grad_out, idx, weight, grad_points, (cudaStream_t)stream); }
+
+// lib/utils/roipool3d/src/roipool3d_kernel.cu:207 (declared in roipool3d.cpp:8-9); runs on the legacy default stream and
+// cudaMalloc/cudaFrees its scratch on every call.
+void roipool3dLauncher(int batch_size, int pts_num, int boxes_num, int feature_in_len, int sampled_pts_num, const float *xyz,
+                       const float *boxes3d, const float *pts_feature, float *pooled_features, int *pooled_empty_flag);
+REF_API void ref_roipool3d(int b, int n, int m, int c, int sampled, const float *xyz, const float *boxes3d, const float *pts_feature,
+                           float *pooled_features, int *pooled_empty_flag)
+{ roipool3dLauncher(b, n, m, c, sampled, xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag); }
