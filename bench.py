@@ -86,6 +86,7 @@ def build_model(impl, device):
     torch.manual_seed(0)
     if impl == "ours":
         model = Pointnet2MSG(config=BackboneConfig())
+        model.auto_fast_inference = False  # bench.py drives the runner explicitly (pipelined); --no-graph times the module path
     else:
         from epnet_b200.pointnet2_utils import make_ops
         from oracle import ref_cuda

@@ -26,6 +26,7 @@ def _models(n_extra_eval_noise=True):
             mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
             mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
             mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    ours.auto_fast_inference = False  # these tests compare the op-by-op module path explicitly
     return ours
 
 
@@ -89,3 +90,26 @@ def test_state_dict_keys_match_reference_naming():
               "Fusion_Conv.0.IA_Layer.conv1.0.weight", "DeConv.3.weight", "image_fusion_conv.bias",
               "final_fusion_img_point.bn1.running_var"):
         assert k in keys, k
+
+
+def test_forward_uses_the_runner_transparently_in_eval_no_grad():
+    """Reference-style calling code (model.eval(); with torch.no_grad(): model(pts, img, xy)) gets the graph runner: same
+    outputs as the op-by-op path, same in-place normalisation of xy, and a weight change invalidates the captured graph."""
+    from epnet_b200 import scenes
+    _strict_fp32()
+    model = _models()
+    data = {k: v.cuda() for k, v in scenes.batch(1040, 2, 16384).items()}
+    with torch.no_grad():
+        xy_slow = data["xy"].clone()
+        xyz_s, f_s = model(data["points"], data["image"], xy_slow)          # auto_fast_inference False: module path
+        model.auto_fast_inference = True
+        xy_fast = data["xy"].clone()
+        xyz_f, f_f = model(data["points"], data["image"], xy_fast)          # runner behind the same call
+        assert len(model._runner_cache) == 1
+        assert torch.equal(xy_fast, xy_slow) and torch.equal(xyz_f, xyz_s)
+        _close(f_f, f_s, 2e-5)
+        model.FP_modules[0].mlp.layer1.conv.weight.mul_(1.5)               # in-place weight edit bumps the version stamp
+        _, f_changed = model(data["points"], data["image"], data["xy"].clone())
+        assert (f_changed - f_f).abs().max().item() > 1e-3 * f_f.abs().max().item()
+    model.train()
+    assert model._runner_cache == {}

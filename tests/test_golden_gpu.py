@@ -60,6 +60,7 @@ def test_small_backbone_on_cuda(path):
     net = Pointnet2MSG(config=small_backbone_config())
     net.load_state_dict(state_dict(g, "w."), strict=True)
     net.cuda().eval()
+    net.auto_fast_inference = False
     pts, img = torch.from_numpy(g["points"]).cuda(), torch.from_numpy(g["image"]).cuda()
     xy = torch.from_numpy(g["xy"]).cuda()
     with torch.no_grad():
