@@ -146,6 +146,7 @@ class BackboneRunner:
 
         self.s_fps = torch.cuda.Stream(device=device)
         self.s_img = torch.cuda.Stream(device=device)
+        self.s_scale = [torch.cuda.Stream(device=device)]  # second grouping scale of a set-abstraction level
         self.kernel_launches_per_replay = 0
         self.graph = None
         self.out = None
@@ -358,17 +359,31 @@ class BackboneRunner:
             ctot = sum(lins[-1].N for _, _, lins in scales)
             width = self.fusion_pm[k].cat_width if c.li_fusion else ctot
             cat = torch.empty((B * npoint, width), **f32)  # [ SA output | (attended) image features ]
-            c_off = 0
-            for radius, ns, lins in scales:
-                bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
-                pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
-                kp = (cin + 3 + 3) // 4 * 4
-                x = torch.empty((B * npoint * ns, kp), **f32)
-                pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, None if feats is None else feats.view(B, n, cin), bidx, x)
-                for lin in lins[:-1]:
-                    x = lin(x, relu=True)
-                lins[-1](x, relu=True, pool=ns, out=cat[:, c_off:c_off + lins[-1].N])  # ReLU + max over nsample in the epilogue
+            # the scales of a level are independent: they run as parallel branches (main stream + side streams), each
+            # writing its own column slice of the level's output
+            fork = torch.cuda.Event()
+            fork.record(main)
+            c_off, joins = 0, []
+            for si, (radius, ns, lins) in enumerate(scales):
+                st = main if si == 0 else self.s_scale[(si - 1) % len(self.s_scale)]
+                with torch.cuda.stream(st):
+                    if st is not main:
+                        st.wait_event(fork)
+                    bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
+                    pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
+                    kp = (cin + 3 + 3) // 4 * 4
+                    x = torch.empty((B * npoint * ns, kp), **f32)
+                    pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, None if feats is None else feats.view(B, n, cin), bidx, x)
+                    for lin in lins[:-1]:
+                        x = lin(x, relu=True)
+                    lins[-1](x, relu=True, pool=ns, out=cat[:, c_off:c_off + lins[-1].N])  # ReLU + max over nsample in the epilogue
+                    if st is not main:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        joins.append(ev)
                 c_off += lins[-1].N
+            for ev in joins:
+                main.wait_event(ev)
             if c.li_fusion:
                 main.wait_event(img_done[k])
                 img = imgs[k]  # NHWC, possibly channel-padded
@@ -443,14 +458,15 @@ class BackboneRunner:
         """Same schedule without the graph (profiling: events around individual launches); single_stream=True also
         serialises the three branches on the current stream so that per-kernel durations are not inflated by overlap."""
         self._load(points, image, xy)
-        saved = (self.s_fps, self.s_img)
+        saved = (self.s_fps, self.s_img, self.s_scale)
         if single_stream:
             self.s_fps = self.s_img = torch.cuda.current_stream(self.device)
+            self.s_scale = [self.s_fps]
         try:
             with torch.no_grad():
                 return self._forward()
         finally:
-            self.s_fps, self.s_img = saved
+            self.s_fps, self.s_img, self.s_scale = saved
 
 
 class PipelinedRunner:
