@@ -147,6 +147,7 @@ class BackboneRunner:
         self.s_fps = torch.cuda.Stream(device=device)
         self.s_img = torch.cuda.Stream(device=device)
         self.s_scale = [torch.cuda.Stream(device=device)]  # second grouping scale of a set-abstraction level
+        self.s_geo = [torch.cuda.Stream(device=device) for _ in range(3)]  # geometry-only work: ball queries (2 scales), three_nn
         self.kernel_launches_per_replay = 0
         self.graph = None
         self.out = None
@@ -263,6 +264,8 @@ class BackboneRunner:
             feats = self._point_stream_pm(main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn)
             main.wait_stream(self.s_fps)
             main.wait_stream(self.s_img)
+            for st in self.s_geo + self.s_scale:
+                main.wait_stream(st)
             return xyz0, feats
 
         # ---- point stream (channel-major, cuBLAS) ----
@@ -350,6 +353,32 @@ class BackboneRunner:
     def _point_stream_pm(self, main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn):
         c, B, N, dev = self.cfg, self.B, self.N, self.device
         f32 = dict(dtype=torch.float32, device=dev)
+        # Geometry-only work depends on the sampled coordinates alone, not on features: every level's ball queries and
+        # three_nn searches are issued on side streams as soon as the FPS level they need is done, off the feature path.
+        bq, nn = {}, {}
+        for si in range(2):
+            with torch.cuda.stream(self.s_geo[si]):
+                for k, (npoint, scales) in enumerate(self.sa_pm):
+                    if si >= len(scales):
+                        continue
+                    radius, ns, _ = scales[si]
+                    self.s_geo[si].wait_event(fps_done[k])
+                    bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
+                    pc.ball_query_wrapper(B, l_xyz[k].shape[1], npoint, radius, ns, l_xyz[k + 1], l_xyz[k], bidx)
+                    ev = torch.cuda.Event()
+                    ev.record(self.s_geo[si])
+                    bq[(k, si)] = (bidx, ev)
+        with torch.cuda.stream(self.s_geo[2]):
+            for k in range(len(self.fp_pm)):
+                self.s_geo[2].wait_event(fps_done[k])
+                unknown, known = l_xyz[k], l_xyz[k + 1]
+                dist2 = torch.empty((B, unknown.shape[1], 3), **f32)
+                idx3 = torch.empty((B, unknown.shape[1], 3), dtype=torch.int32, device=dev)
+                pc.three_nn_wrapper(B, unknown.shape[1], known.shape[1], unknown, known, dist2, idx3)
+                ev = torch.cuda.Event()
+                ev.record(self.s_geo[2])
+                nn[k] = (dist2, idx3, ev)
+
         l_feat = [None]  # (B*n_k, C_k) point-major
         for k, (npoint, scales) in enumerate(self.sa_pm):
             main.wait_event(fps_done[k])
@@ -369,8 +398,12 @@ class BackboneRunner:
                 with torch.cuda.stream(st):
                     if st is not main:
                         st.wait_event(fork)
-                    bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
-                    pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
+                    if (k, si) in bq:
+                        bidx, bq_ev = bq[(k, si)]
+                        st.wait_event(bq_ev)
+                    else:  # more than two scales: query here
+                        bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
+                        pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
                     kp = (cin + 3 + 3) // 4 * 4
                     x = torch.empty((B * npoint * ns, kp), **f32)
                     pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, None if feats is None else feats.view(B, n, cin), bidx, x)
@@ -400,9 +433,8 @@ class BackboneRunner:
             skip, kf = l_feat[i - 1], l_feat[i]
             c1 = 0 if skip is None else skip.shape[1]
             c2 = kf.shape[1]
-            dist2 = torch.empty((B, n, 3), **f32)
-            idx3 = torch.empty((B, n, 3), dtype=torch.int32, device=dev)
-            pc.three_nn_wrapper(B, n, m, unknown, known, dist2, idx3)
+            dist2, idx3, nn_ev = nn[len(self.fp_pm) + i]  # searched on the geometry stream right after the FPS level
+            main.wait_event(nn_ev)
             x = torch.empty((B * n, c2 + c1), **f32)
             pc.three_interpolate_concat_pm_wrapper(B, c2, m, n, c1, kf, idx3, dist2, skip, x)
             lins = self.fp_pm[i]
@@ -458,15 +490,16 @@ class BackboneRunner:
         """Same schedule without the graph (profiling: events around individual launches); single_stream=True also
         serialises the three branches on the current stream so that per-kernel durations are not inflated by overlap."""
         self._load(points, image, xy)
-        saved = (self.s_fps, self.s_img, self.s_scale)
+        saved = (self.s_fps, self.s_img, self.s_scale, self.s_geo)
         if single_stream:
             self.s_fps = self.s_img = torch.cuda.current_stream(self.device)
             self.s_scale = [self.s_fps]
+            self.s_geo = [self.s_fps] * 3
         try:
             with torch.no_grad():
                 return self._forward()
         finally:
-            self.s_fps, self.s_img, self.s_scale = saved
+            self.s_fps, self.s_img, self.s_scale, self.s_geo = saved
 
 
 class PipelinedRunner:
