@@ -131,6 +131,7 @@ def sweep_rooflines(device, peak):
     idx3 = torch.randint(0, m, (1, n, 3), generator=g).int().to(device)
     d2 = torch.rand(1, n, 3, generator=g).to(device)
     out = torch.empty(n, C2, device=device)
+    d2 = d2 / d2.sum(-1, keepdim=True)  # normalised weights
     t = _event_time(lambda: pc.three_interpolate_concat_pm_wrapper(1, C2, m, n, 0, known, idx3, d2, None, out))
     by = 4 * C2 * min(m, 3 * n) + 24 * n + 4 * C2 * n
     rows.append({"op": "three_interpolate_concat_pm", "shape": [1, C2, m, n], "us": round(t * 1e6, 1), "algorithmic_mb": round(by / 1e6, 1),

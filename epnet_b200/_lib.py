@@ -28,7 +28,9 @@ SIGNATURES = {
     "epnet_bias_relu_maxpool": [_c_int] * 4 + [_c_void_p] * 3 + [_c_ll, _c_void_p],
     "epnet_three_interpolate_concat": [_c_int] * 5 + [_c_void_p] * 6,
     "epnet_group_concat_pm": [_c_int] * 5 + [_c_void_p] * 3 + [_c_int, _c_void_p, _c_void_p, _c_int, _c_void_p],
-    "epnet_three_interpolate_concat_pm": [_c_int] * 5 + [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_three_interpolate_concat_pm": [_c_int] * 5 + [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int,
+                                          _c_void_p],
+    "epnet_three_nn_weights": [_c_int] * 3 + [_c_void_p] * 6,
     "epnet_grid_gather_pm": [_c_int] * 5 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_conv3x3_nhwc_tf32x3": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_grid_gather_nhwc_pm": [_c_int] * 5 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],

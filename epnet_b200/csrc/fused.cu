@@ -259,56 +259,71 @@ __device__ __forceinline__ PmMap pm_map(int group_shift)
 }
 
 // out[(b,p,s)][0..C) = feats[b, idx[b,p,s], 0..C) ; out[..][C..C+3) = xyz[b, idx] - new_xyz[b,p]
+// A lane owns one 16-byte chunk position of FOUR consecutive rows (a "quad": same centre when nsample % 4 == 0): one 128-bit index
+// load, one division, four independent row gathers in flight.
 __global__ void __launch_bounds__(256)
 group_concat_pm_kernel(int c, int n, int m, int ns, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                        const float *__restrict__ feats, int ldf, const int *__restrict__ idx, float *__restrict__ out, int ldo,
-                       long long rows_total, int chunks, int vec_ok, int group_shift)
+                       int quads_total, int chunks, int vec_ok, int group_shift)
 {
-    const PmMap map = pm_map(group_shift);
-    if (map.row >= rows_total) return;
-    const int centre = (int)(map.row / ns);            // b*m + p
+    const unsigned lane_global = blockIdx.x * blockDim.x + threadIdx.x;
+    const int quad = (int)(lane_global >> group_shift);
+    if (quad >= quads_total) return;
+    const int chunk0 = (int)(lane_global & ((1u << group_shift) - 1u)), step = 1 << group_shift;
+    const int row0 = quad * 4;
+    const int centre = row0 / ns;  // b*m + p, shared by the quad
     const int scene = centre / m;
-    const int src = __ldg(idx + map.row);
-    const float *frow = feats + ((size_t)scene * n + src) * ldf;
-    const float *prow = xyz + ((size_t)scene * n + src) * 3;
+    const int4 src = __ldg(reinterpret_cast<const int4 *>(idx + row0));
+    const int srcs[4] = {src.x, src.y, src.z, src.w};
+    const float *fbase = feats + (size_t)scene * n * ldf;
+    const float *pbase = xyz + (size_t)scene * n * 3;
     const float *crow = new_xyz + (size_t)centre * 3;
-    float *orow = out + (size_t)map.row * ldo;
-    for (int ch = map.chunk0; ch < chunks; ch += map.step) {
+    float *orow = out + (size_t)row0 * ldo;
+    for (int ch = chunk0; ch < chunks; ch += step) {
         const int k0 = ch * 4;
-        float4 v;
+        float4 v[4];
         if (vec_ok && k0 + 4 <= c) {
-            v = __ldg(reinterpret_cast<const float4 *>(frow + k0));
-        } else {
-            float e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + j;
-                if (k < c) e[j] = __ldg(frow + k);
-                else if (k < c + 3) e[j] = __fsub_rn(__ldg(prow + (k - c)), __ldg(crow + (k - c)));
-                else e[j] = 0.f;
+            for (int r = 0; r < 4; ++r) v[r] = __ldg(reinterpret_cast<const float4 *>(fbase + (size_t)srcs[r] * ldf + k0));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + j;
+                    if (k < c) e[j] = __ldg(fbase + (size_t)srcs[r] * ldf + k);
+                    else if (k < c + 3) e[j] = __fsub_rn(__ldg(pbase + (size_t)srcs[r] * 3 + (k - c)), __ldg(crow + (k - c)));
+                    else e[j] = 0.f;
+                }
+                v[r] = make_float4(e[0], e[1], e[2], e[3]);
             }
-            v = make_float4(e[0], e[1], e[2], e[3]);
         }
-        __stcs(reinterpret_cast<float4 *>(orow + k0), v);  // streamed: consumed once by the GEMM producer
+#pragma unroll
+        for (int r = 0; r < 4; ++r) __stcs(reinterpret_cast<float4 *>(orow + (size_t)r * ldo + k0), v[r]);  // streamed: read once by the GEMM
     }
 }
 
 // out[(b,i)][0..C2) = sum_k w_k * known[b, idx[b,i,k], :] ; out[..][C2..C2+C1) = skip[b,i,:]
+// `weight` = the normalised inverse-distance weights (epnet_three_nn_weights) when from_dist2 == 0, else squared distances
 __global__ void __launch_bounds__(256)
 three_interpolate_concat_pm_kernel(int c2, int m, int n, int c1, const float *__restrict__ known, int ldk, const int *__restrict__ idx,
-                                   const float *__restrict__ dist2, const float *__restrict__ skip, int lds, float *__restrict__ out,
-                                   int ldo, long long rows_total, int chunks, int group_shift)
+                                   const float *__restrict__ weight, int from_dist2, const float *__restrict__ skip, int lds,
+                                   float *__restrict__ out, int ldo, long long rows_total, int chunks, int group_shift)
 {
     const PmMap map = pm_map(group_shift);
     if (map.row >= rows_total) return;
     const long long row = map.row;
     const int scene = (int)(row / n);
     const int i0 = __ldg(idx + row * 3), i1 = __ldg(idx + row * 3 + 1), i2 = __ldg(idx + row * 3 + 2);
-    const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3)), 1e-8f));
-    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 1)), 1e-8f));
-    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(dist2 + row * 3 + 2)), 1e-8f));
-    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
-    const float w0 = __fdiv_rn(r0, norm), w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm);
+    float w0 = __ldg(weight + row * 3), w1 = __ldg(weight + row * 3 + 1), w2 = __ldg(weight + row * 3 + 2);
+    if (from_dist2) {
+        const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(w0), 1e-8f));
+        const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(w1), 1e-8f));
+        const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(w2), 1e-8f));
+        const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+        w0 = __fdiv_rn(r0, norm); w1 = __fdiv_rn(r1, norm); w2 = __fdiv_rn(r2, norm);
+    }
     const float *kb = known + (size_t)scene * m * ldk;
     const float *ka = kb + (size_t)i0 * ldk, *kbb = kb + (size_t)i1 * ldk, *kc = kb + (size_t)i2 * ldk;
     float *orow = out + (size_t)row * ldo;
@@ -401,22 +416,25 @@ EPNET_API int epnet_group_concat_pm(int b, int c, int n, int m, int nsample, con
     using namespace epnet;
     if (b < 0 || c < 0 || n < 0 || m < 0 || nsample < 0 || !xyz || !new_xyz || !idx || !out || (c > 0 && !feats)) return EPNET_ERR_BAD_ARG;
     if (ldo < c + 3 || (ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return EPNET_ERR_BAD_ARG;
+    if ((nsample & 3) || (reinterpret_cast<uintptr_t>(idx) & 15)) return EPNET_ERR_BAD_ARG;  // quads of 4 samples share a centre
     const long long rows = (long long)b * m * nsample;
     if (rows == 0) return EPNET_OK;
+    if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
     const int chunks = (c + 3 + 3) / 4;
     const int vec_ok = c > 0 && (ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
     const int gs = pm_group_shift(chunks);
-    const long long threads = rows << gs;
+    const long long threads = (rows / 4) << gs;
     group_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c, n, m, nsample, xyz, new_xyz, feats, ldf, idx,
-                                                                                            out, ldo, rows, chunks, vec_ok, gs);
+                                                                                            out, ldo, (int)(rows / 4), chunks, vec_ok, gs);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
 EPNET_API int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int c1, const float *known, int ldk, const int *idx,
-                                                const float *dist2, const float *skip, int lds, float *out, int ldo, void *stream)
+                                                const float *weight, int from_dist2, const float *skip, int lds, float *out, int ldo,
+                                                void *stream)
 {
     using namespace epnet;
-    if (b < 0 || c2 <= 0 || c1 < 0 || m < 0 || n < 0 || !known || !idx || !dist2 || !out || (c1 > 0 && !skip)) return EPNET_ERR_BAD_ARG;
+    if (b < 0 || c2 <= 0 || c1 < 0 || m < 0 || n < 0 || !known || !idx || !weight || !out || (c1 > 0 && !skip)) return EPNET_ERR_BAD_ARG;
     if ((c2 & 3) || (c1 & 3) || (ldk & 3) || (ldo & 3) || (c1 > 0 && (lds & 3)) || ldo < c1 + c2) return EPNET_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(known) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(skip)) & 15) return EPNET_ERR_BAD_ARG;
     const long long rows = (long long)b * n;
@@ -424,8 +442,8 @@ EPNET_API int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int
     const int chunks = (c1 + c2) / 4;
     const int gs = pm_group_shift(chunks);
     const long long threads = rows << gs;
-    three_interpolate_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2, m, n, c1, known, ldk, idx, dist2,
-                                                                                                        skip, lds, out, ldo, rows, chunks, gs);
+    three_interpolate_concat_pm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        c2, m, n, c1, known, ldk, idx, weight, from_dist2, skip, lds, out, ldo, rows, chunks, gs);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 

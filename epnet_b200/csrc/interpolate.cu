@@ -40,7 +40,7 @@ __device__ __forceinline__ void top3_insert(Top3 &t, float d, int k)
 
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known, float *__restrict__ dist2,
-                int *__restrict__ idx, int use_bulk)
+                int *__restrict__ idx, int use_bulk, float *__restrict__ weight)
 {
     __shared__ __align__(128) float tile[2][kNnTile * 3];
     __shared__ __align__(8) uint64_t full[2];
@@ -50,6 +50,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     known += (size_t)scene * m * 3;
     dist2 += (size_t)scene * n * 3;
     idx += (size_t)scene * n * 3;
+    if (weight) weight += (size_t)scene * n * 3;
 
     const int q = blockIdx.x * kNnThreads + threadIdx.x;
     const bool live = q < n;
@@ -114,6 +115,14 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     if (live) {
         dist2[3 * q] = best.d0; dist2[3 * q + 1] = best.d1; dist2[3 * q + 2] = best.d2;
         idx[3 * q] = best.i0;   idx[3 * q + 1] = best.i1;   idx[3 * q + 2] = best.i2;
+        if (weight) {
+            // inverse-distance weights of PointnetFPModule (pointnet2_utils.py:98 sqrt, pointnet2_modules.py:157-159), once per query
+            const float r0 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best.d0), 1e-8f));
+            const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best.d1), 1e-8f));
+            const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(best.d2), 1e-8f));
+            const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+            weight[3 * q] = __fdiv_rn(r0, norm); weight[3 * q + 1] = __fdiv_rn(r1, norm); weight[3 * q + 2] = __fdiv_rn(r2, norm);
+        }
     }
 }
 
@@ -213,7 +222,21 @@ EPNET_API int epnet_three_nn(int b, int n, int m, const float *unknown, const fl
     if (b == 0 || n == 0) return EPNET_OK;
     const int use_bulk = m > 0 && ((reinterpret_cast<uintptr_t>(known) & 15) == 0) && (m % 4 == 0);
     dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
-    three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, use_bulk);
+    three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, use_bulk, nullptr);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+// three_nn that also emits the normalised inverse-distance weights the feature-propagation module derives from the
+// distances (pointnet2_modules.py:157-159), so the interpolation kernel does not recompute them per channel chunk
+EPNET_API int epnet_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, float *weight,
+                                     void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || n < 0 || m < 0 || !unknown || !known || !dist2 || !idx || !weight) return EPNET_ERR_BAD_ARG;
+    if (b == 0 || n == 0) return EPNET_OK;
+    const int use_bulk = m > 0 && ((reinterpret_cast<uintptr_t>(known) & 15) == 0) && (m % 4 == 0);
+    dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
+    three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, use_bulk, weight);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 

@@ -166,10 +166,15 @@ def group_concat_pm_wrapper(b, c, n, m, nsample, xyz, new_xyz, feats_pm, idx, ou
           _opt(feats_pm, torch.float32, "feats_pm"), ldf, _i(idx, "idx"), out.data_ptr(), out.stride(0))
 
 
-def three_interpolate_concat_pm_wrapper(b, c2, m, n, c1, known_pm, idx, dist2, skip_pm, out):
+def three_interpolate_concat_pm_wrapper(b, c2, m, n, c1, known_pm, idx, weight, skip_pm, out, from_dist2=False):
     _call("three_interpolate_concat_pm", LIB.epnet_three_interpolate_concat_pm, known_pm, b, c2, m, n, c1, known_pm.data_ptr(),
-          known_pm.stride(-2), _i(idx, "idx"), _f(dist2, "dist2"), None if skip_pm is None else skip_pm.data_ptr(),
+          known_pm.stride(-2), _i(idx, "idx"), _f(weight, "weight"), int(bool(from_dist2)), None if skip_pm is None else skip_pm.data_ptr(),
           0 if skip_pm is None else skip_pm.stride(-2), out.data_ptr(), out.stride(0))
+
+
+def three_nn_weights_wrapper(b, n, m, unknown, known, dist2, idx, weight):
+    _call("three_nn_weights", LIB.epnet_three_nn_weights, unknown, b, n, m, _f(unknown, "unknown"), _f(known, "known"),
+          _f(dist2, "dist2"), _i(idx, "idx"), _f(weight, "weight"))
 
 
 def grid_gather_pm_wrapper(b, c, h, w, n, fmap, xy, align_corners, out):

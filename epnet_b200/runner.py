@@ -374,10 +374,11 @@ class BackboneRunner:
                 unknown, known = l_xyz[k], l_xyz[k + 1]
                 dist2 = torch.empty((B, unknown.shape[1], 3), **f32)
                 idx3 = torch.empty((B, unknown.shape[1], 3), dtype=torch.int32, device=dev)
-                pc.three_nn_wrapper(B, unknown.shape[1], known.shape[1], unknown, known, dist2, idx3)
+                wts = torch.empty((B, unknown.shape[1], 3), **f32)
+                pc.three_nn_weights_wrapper(B, unknown.shape[1], known.shape[1], unknown, known, dist2, idx3, wts)
                 ev = torch.cuda.Event()
                 ev.record(self.s_geo[2])
-                nn[k] = (dist2, idx3, ev)
+                nn[k] = (wts, idx3, ev)
 
         l_feat = [None]  # (B*n_k, C_k) point-major
         for k, (npoint, scales) in enumerate(self.sa_pm):
@@ -433,10 +434,10 @@ class BackboneRunner:
             skip, kf = l_feat[i - 1], l_feat[i]
             c1 = 0 if skip is None else skip.shape[1]
             c2 = kf.shape[1]
-            dist2, idx3, nn_ev = nn[len(self.fp_pm) + i]  # searched on the geometry stream right after the FPS level
+            wts, idx3, nn_ev = nn[len(self.fp_pm) + i]  # searched on the geometry stream right after the FPS level
             main.wait_event(nn_ev)
             x = torch.empty((B * n, c2 + c1), **f32)
-            pc.three_interpolate_concat_pm_wrapper(B, c2, m, n, c1, kf, idx3, dist2, skip, x)
+            pc.three_interpolate_concat_pm_wrapper(B, c2, m, n, c1, kf, idx3, wts, skip, x)
             lins = self.fp_pm[i]
             last_out = None
             if i - 1 == -(len(self.fp_pm) + 1) and c.li_fusion:  # level 0: write straight into the final fusion's concat buffer

@@ -118,12 +118,18 @@ int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, const float 
  * operand of epnet_gemm_tf32x3 directly and read each gathered point as one contiguous row.
  * group_concat_pm: out[(b,p,s)] = [ feats[b, idx[b,p,s], 0..C) | xyz[b, idx] - new_xyz[b,p] | 0-pad ], row stride ldo
  *   (QueryAndGroup.forward, pointnet2_utils.py:250-257, with the xyz channels AFTER the features).
- * three_interpolate_concat_pm: out[(b,i)] = [ interpolated known feats (C2) | skip feats (C1) ] (pointnet2_modules.py:157-166).
+ * three_interpolate_concat_pm: out[(b,i)] = [ interpolated known feats (C2) | skip feats (C1) ] (pointnet2_modules.py:157-166);
+ *   `weight` holds the normalised weights, or the squared distances when from_dist2 != 0.
  * grid_gather_pm: out[(b,i)][0..C) = bilinear(fmap[b,:,.,.], xy[b,i]) (Feature_Gather, lib/net/pointnet2_msg.py:107-120). */
 int epnet_group_concat_pm(int b, int c, int n, int m, int nsample, const float *xyz, const float *new_xyz, const float *feats, int ldf,
                           const int *idx, float *out, int ldo, void *stream);
 int epnet_three_interpolate_concat_pm(int b, int c2, int m, int n, int c1, const float *known, int ldk, const int *idx,
-                                      const float *dist2, const float *skip, int lds, float *out, int ldo, void *stream);
+                                      const float *weight, int from_dist2, const float *skip, int lds, float *out, int ldo,
+                                      void *stream);
+/* three_nn (same search, same outputs as epnet_three_nn) that also writes weight (B,n,3): the normalised inverse-distance
+ * weights of pointnet2_modules.py:157-159, consumed by epnet_three_interpolate_concat_pm with from_dist2 = 0. */
+int epnet_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, float *weight,
+                           void *stream);
 int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, int ldo,
                          void *stream);
 

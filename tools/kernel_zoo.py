@@ -43,7 +43,7 @@ for _ in range(reps):
     idx3 = torch.randint(0, m, (1, n, 3), generator=g).int().to(dev)
     dd = torch.rand(1, n, 3, generator=g).to(dev)
     o = torch.empty(n, C2, device=dev)
-    pc.three_interpolate_concat_pm_wrapper(1, C2, m, n, 0, known_pm, idx3, dd, None, o)
+    pc.three_interpolate_concat_pm_wrapper(1, C2, m, n, 0, known_pm, idx3, dd, None, o, from_dist2=True)
     w = torch.rand(1, n, 3, generator=g).to(dev)
     o_cm = torch.empty(1, C2, n, device=dev)
     pc.three_interpolate_wrapper(1, C2, m, n, known_pm.transpose(1, 2).contiguous(), idx3, w, o_cm)
