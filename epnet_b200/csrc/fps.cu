@@ -25,7 +25,6 @@
 // cached winners in the registers of lanes 0..7.  One __syncthreads per iteration (none when a single
 // warp holds the whole cloud, N <= 256).  16384 < N <= 131072 spreads a scene over a thread-block cluster (DSMEM exchange of
 // the per-CTA winners); beyond that coordinates stream from L2 (fps_streaming_kernel).
-#include <cstdlib>
 #include "common.cuh"
 
 namespace epnet {
@@ -573,16 +572,12 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
 #define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st
-        static const int variant = getenv("EPNET_FPS_VARIANT") ? atoi(getenv("EPNET_FPS_VARIANT")) : 0;  // tuning knob
-        if (n <= 256) return launch_bucket<1, 8, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32
+        if (n <= 256) return launch_bucket<1, 8, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32, one warp, no barrier
         if (n <= 1024) return launch_bucket<4, 8, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
-        if (n <= 4096) {
-            if (variant == 1) return launch_bucket<8, 16, 1>(EPNET_FPS_ARGS);  // 128 buckets of 32, 8 warps
-            if (variant == 2) return launch_bucket<4, 8, 4>(EPNET_FPS_ARGS);   //  32 buckets of 128, 4 warps
-            return launch_bucket<16, 8, 1>(EPNET_FPS_ARGS);                    // 128 buckets of 32
-        }
-        if (variant == 1) return launch_bucket<8, 16, 4>(EPNET_FPS_ARGS);      // 128 buckets of 128, 8 warps
-        return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                        // 128 buckets of 128
+        if (n <= 4096) return launch_bucket<16, 8, 1>(EPNET_FPS_ARGS);  // 128 buckets of  32
+        return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
+        // (measured alternatives: 8 warps x 16 buckets is 27 % slower at N = 16384 -- touched buckets of one warp update
+        //  serially -- and 4 warps x 8 buckets x 128 points is 25 % slower at N = 4096)
 #undef EPNET_FPS_ARGS
     }
     if (n <= 8 * kFpsMaxResident) {
