@@ -345,6 +345,7 @@ fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict_
     float cx = __ldg(xyz_scene), cy = __ldg(xyz_scene + 1), cz = __ldg(xyz_scene + 2);  // sample 0 is point 0 of the scene
     uint32_t warp_bits = lane < kBuckets ? bmax : 0u, warp_key = lane < kBuckets ? bkey : 0xffffffffu;
     warp_argmax(warp_bits, warp_key);
+    const uint32_t slot_wr = smem_u32(&slots[0][warp]), slot_rd = smem_u32(&slots[0][lane & 31]);
     for (int j = 1; j < m; ++j) {
         // which buckets can change?  box distance (deflated) vs the bucket's largest running distance
         const float ex = fmaxf(fmaxf(blo_x - cx, cx - bhi_x), 0.f);
@@ -353,6 +354,7 @@ fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict_
         const float lb = (ex * ex + ey * ey + ez * ez) * kBoxDeflate;
         const bool active = lane < kBuckets && lb < __uint_as_float(bmax);
         const uint32_t mask = __ballot_sync(0xffffffffu, active);
+        if (mask) {  // most warps, most iterations: nothing to update -> straight to the exchange
 #pragma unroll
         for (int b = 0; b < kBuckets; ++b) {
             if (mask & (1u << b)) {  // warp-uniform
@@ -384,21 +386,19 @@ fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict_
             }
         }
         // winner of the warp's buckets (unchanged if none of them was touched), then of the CTA
-        if (mask) {
             warp_bits = lane < kBuckets ? bmax : 0u;
             warp_key = lane < kBuckets ? bkey : 0xffffffffu;
             warp_argmax(warp_bits, warp_key);
         }
         uint32_t wbits = warp_bits, wkey = warp_key;
         if (NW > 1) {
-            const int par = j & 1;
-            if (lane == 0) {
-                slots[par][warp].dist_bits = wbits;
-                slots[par][warp].tie = wkey;
-            }
+            // shared-space addresses computed once outside the loop (no generic->shared conversion per iteration)
+            const uint32_t par_off = (uint32_t)(j & 1) * 32u * 8u;
+            if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot_wr + par_off), "r"(wbits), "r"(wkey) : "memory");
             __syncthreads();
-            wbits = lane < NW ? slots[par][lane].dist_bits : 0u;
-            wkey = lane < NW ? slots[par][lane].tie : 0xffffffffu;
+            wbits = 0u;
+            wkey = 0xffffffffu;
+            if (lane < NW) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wbits), "=r"(wkey) : "r"(slot_rd + par_off) : "memory");
             warp_argmax(wbits, wkey);
         }
         const uint32_t pos = wkey & PMASK;
