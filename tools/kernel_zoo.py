@@ -8,7 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from epnet_b200 import pointnet2_cuda as pc  # noqa: E402
 from epnet_b200 import scenes  # noqa: E402
-from epnet_b200.gemm import PackedLinear  # noqa: E402
+from epnet_b200.gemm import PackedConv3x3, PackedLinear  # noqa: E402
+from epnet_b200 import roipool3d_utils  # noqa: E402
 
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
@@ -59,5 +60,24 @@ for _ in range(reps):
     lin(X, relu=True)
     lin2 = PackedLinear(torch.randn(128, 96, device=dev) / 9.8, torch.zeros(128, device=dev))
     lin2(X[:, :96], relu=True, pool=32)
+    # --- implicit-GEMM 3x3 convolution (image stream, 128->256 at 96x320, batch 2), NHWC gather, deconv shuffle
+    ximg = torch.randn(2, 96, 320, 128, device=dev)
+    conv = PackedConv3x3(torch.randn(256, 128, 3, 3, device=dev) / 34, torch.zeros(256, device=dev), stride=1)
+    yimg = conv(ximg, relu=True)
+    xyp = (torch.rand(2, 16384, 2, generator=g) * 2 - 1).to(dev)
+    gout = torch.empty(2 * 16384, 256, device=dev)
+    pc.grid_gather_nhwc_pm_wrapper(2, 256, 96, 320, 16384, yimg, xyp, False, gout)
+    ydec = torch.randn(2 * 96 * 320, 4 * 4 * 16, device=dev)
+    cat = torch.empty(2, 384, 1280, 64, device=dev)
+    pc.deconv_shuffle_nhwc_wrapper(2, 96, 320, 4, 16, ydec, cat, 16)
+    # --- RoI pooling and the cluster (DSMEM) FPS at N = 131072
+    boxes = torch.zeros(2, 64, 7, device=dev)
+    boxes[..., 0] = torch.linspace(-20, 20, 64, device=dev); boxes[..., 1] = 1.8; boxes[..., 2] = torch.linspace(5, 60, 64, device=dev)
+    boxes[..., 3:6] = torch.tensor([1.6, 1.7, 4.0], device=dev); boxes[..., 6] = 0.3
+    roipool3d_utils.roipool3d_gpu(pts, torch.randn(2, 16384, 128, device=dev), boxes, 1.0)
+    big = torch.rand(1, 131072, 3, device=dev) * torch.tensor([80.0, 4.0, 70.0], device=dev)
+    tb = torch.full((1, 131072), 1e10, device=dev)
+    ib = torch.empty(1, 1024, dtype=torch.int32, device=dev)
+    pc.furthest_point_sampling_wrapper(1, 131072, 1024, big, tb, ib)
 torch.cuda.synchronize()
 print("zoo ok")
