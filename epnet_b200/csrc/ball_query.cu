@@ -15,8 +15,8 @@
 namespace epnet {
 
 constexpr int kBqWarps = 8;
-constexpr int kBqCentresPerWarp = 4;
-constexpr int kBqCentresPerCta = kBqWarps * kBqCentresPerWarp;  // 32
+constexpr int kBqCentresPerWarp = 2;
+constexpr int kBqCentresPerCta = kBqWarps * kBqCentresPerWarp;  // 16
 constexpr int kBqTile = 1920;                                  // points per stage (22.5 KB); two stages stay under the 48 KB static limit
 
 __global__ void __launch_bounds__(kBqWarps * 32)

@@ -15,11 +15,30 @@ namespace epnet {
 // ---------------------------------------------------------------------------------------------
 constexpr int kNnThreads = 128;
 constexpr int kNnTile = 1920;
+constexpr int kNnSlices = 4;  // lanes per query: each scans every 4th group of 4 staged points, partial top-3s merged by shuffle
 
 struct Top3 {
     float d0, d1, d2;
     int i0, i1, i2;
 };
+
+// lexicographic (d, k) insertion: used to merge partial results, where index order is no longer implied by arrival order
+__device__ __forceinline__ void top3_insert_lex(Top3 &t, float d, int k)
+{
+    if (d < t.d2 || (d == t.d2 && k < t.i2)) {
+        if (d < t.d1 || (d == t.d1 && k < t.i1)) {
+            t.d2 = t.d1; t.i2 = t.i1;
+            if (d < t.d0 || (d == t.d0 && k < t.i0)) {
+                t.d1 = t.d0; t.i1 = t.i0;
+                t.d0 = d; t.i0 = k;
+            } else {
+                t.d1 = d; t.i1 = k;
+            }
+        } else {
+            t.d2 = d; t.i2 = k;
+        }
+    }
+}
 
 __device__ __forceinline__ void top3_insert(Top3 &t, float d, int k)
 {
@@ -52,7 +71,8 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     idx += (size_t)scene * n * 3;
     if (weight) weight += (size_t)scene * n * 3;
 
-    const int q = blockIdx.x * kNnThreads + threadIdx.x;
+    const int q = blockIdx.x * (kNnThreads / kNnSlices) + (threadIdx.x / kNnSlices);
+    const int slice = threadIdx.x % kNnSlices;
     const bool live = q < n;
     const float ux = live ? __ldg(unknown + 3 * q) : 0.f;
     const float uy = live ? __ldg(unknown + 3 * q + 1) : 0.f;
@@ -91,8 +111,8 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
             __syncthreads();
         }
         const float *tp = tile[buf];
-        int p = 0;
-        for (; p + 4 <= count; p += 4) {
+        const int full = count & ~3;
+        for (int p = slice * 4; p < full; p += 4 * kNnSlices) {
             // 12 consecutive floats = 3 x LDS.128 (tile rows are 48 B, p % 4 == 0 keeps 16-byte alignment)
             const float4 a = *reinterpret_cast<const float4 *>(tp + 3 * p);
             const float4 b = *reinterpret_cast<const float4 *>(tp + 3 * p + 4);
@@ -102,17 +122,29 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
             const float d2 = sqdist_ref(ux, uy, uz, b.z, b.w, c.x);
             const float d3 = sqdist_ref(ux, uy, uz, c.y, c.z, c.w);
             const float lo = fminf(fminf(d0, d1), fminf(d2, d3));
-            if (lo < best.d2) {  // rare once the three bests have settled; order of insertion = index order
+            if (lo < best.d2) {  // rare once the three bests have settled; within a slice indices arrive in ascending order
                 top3_insert(best, d0, base + p);
                 top3_insert(best, d1, base + p + 1);
                 top3_insert(best, d2, base + p + 2);
                 top3_insert(best, d3, base + p + 3);
             }
         }
-        for (; p < count; ++p) top3_insert(best, sqdist_ref(ux, uy, uz, tp[3 * p], tp[3 * p + 1], tp[3 * p + 2]), base + p);
+        if (slice == 0)
+            for (int p = full; p < count; ++p) top3_insert_lex(best, sqdist_ref(ux, uy, uz, tp[3 * p], tp[3 * p + 1], tp[3 * p + 2]), base + p);
         __syncthreads();  // buffer `buf` may be refilled from the next iteration on
     }
-    if (live) {
+    // merge the kNnSlices partial top-3s of a query (adjacent lanes) -- lexicographic (d, k) is exactly the reference's order
+#pragma unroll
+    for (int step = 1; step < kNnSlices; step <<= 1) {
+        const float e0 = __shfl_xor_sync(0xffffffffu, best.d0, step), e1 = __shfl_xor_sync(0xffffffffu, best.d1, step),
+                    e2 = __shfl_xor_sync(0xffffffffu, best.d2, step);
+        const int j0 = __shfl_xor_sync(0xffffffffu, best.i0, step), j1 = __shfl_xor_sync(0xffffffffu, best.i1, step),
+                  j2 = __shfl_xor_sync(0xffffffffu, best.i2, step);
+        top3_insert_lex(best, e0, j0);
+        top3_insert_lex(best, e1, j1);
+        top3_insert_lex(best, e2, j2);
+    }
+    if (live && slice == 0) {
         dist2[3 * q] = best.d0; dist2[3 * q + 1] = best.d1; dist2[3 * q + 2] = best.d2;
         idx[3 * q] = best.i0;   idx[3 * q + 1] = best.i1;   idx[3 * q + 2] = best.i2;
         if (weight) {
@@ -221,7 +253,7 @@ EPNET_API int epnet_three_nn(int b, int n, int m, const float *unknown, const fl
     if (b < 0 || n < 0 || m < 0 || !unknown || !known || !dist2 || !idx) return EPNET_ERR_BAD_ARG;
     if (b == 0 || n == 0) return EPNET_OK;
     const int use_bulk = m > 0 && ((reinterpret_cast<uintptr_t>(known) & 15) == 0) && (m % 4 == 0);
-    dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
+    dim3 grid((n + kNnThreads / kNnSlices - 1) / (kNnThreads / kNnSlices), b);
     three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, use_bulk, nullptr);
     EPNET_RETURN_LAUNCH_STATUS();
 }
@@ -235,7 +267,7 @@ EPNET_API int epnet_three_nn_weights(int b, int n, int m, const float *unknown, 
     if (b < 0 || n < 0 || m < 0 || !unknown || !known || !dist2 || !idx || !weight) return EPNET_ERR_BAD_ARG;
     if (b == 0 || n == 0) return EPNET_OK;
     const int use_bulk = m > 0 && ((reinterpret_cast<uintptr_t>(known) & 15) == 0) && (m % 4 == 0);
-    dim3 grid((n + kNnThreads - 1) / kNnThreads, b);
+    dim3 grid((n + kNnThreads / kNnSlices - 1) / (kNnThreads / kNnSlices), b);
     three_nn_kernel<<<grid, kNnThreads, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, use_bulk, weight);
     EPNET_RETURN_LAUNCH_STATUS();
 }
