@@ -1,0 +1,94 @@
+"""BASELINE.json configs[4]: op-level sweep (N 4k..128k, npoint = N/4, nsample 16/32, C 64/256), the B200 kernels next to the
+reference's own kernels on the same GPU.  One JSON row per (op, shape): microseconds, speed-up, algorithmic GB/s and fraction
+of the measured HBM peak for the memory-bound ops."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench_roofline as br  # noqa: E402
+from epnet_b200 import pointnet2_cuda as ours  # noqa: E402
+from oracle import ref_cuda  # noqa: E402
+
+dev = torch.device("cuda:0")
+peak, _ = br.hbm_peak()
+g = torch.Generator().manual_seed(0)
+rows = []
+
+
+def t(fn, it=5):
+    fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(it):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / it * 1e3
+
+
+def rec(op, shape, f_ours, f_ref, by=None):
+    r = {"op": op, "shape": shape, "ours_us": round(t(f_ours), 1)}
+    if f_ref is not None:
+        r["ref_us"] = round(t(f_ref, it=2), 1)
+        r["speedup"] = round(r["ref_us"] / r["ours_us"], 2)
+    if by:
+        r["algorithmic_gbs"] = round(by / r["ours_us"] / 1e3, 1)
+        r["frac_hbm"] = round(by / r["ours_us"] / 1e3 / peak, 3)
+    rows.append(r)
+    print(r, flush=True)
+
+
+for N in (4096, 16384, 65536, 131072):
+    M = N // 4
+    xyz = (torch.rand(1, N, 3, generator=g) * torch.tensor([80.0, 4.0, 70.0])).to(dev)
+    temp = torch.empty(1, N, device=dev)
+    idx = torch.empty(1, M, dtype=torch.int32, device=dev)
+
+    def fps(be):
+        temp.fill_(1e10)
+        be.furthest_point_sampling_wrapper(1, N, M, xyz, temp, idx)
+    rec("fps", [1, N, M], lambda: fps(ours), lambda: fps(ref_cuda))
+    rows[-1]["ours_ns_per_iter"] = round(rows[-1]["ours_us"] * 1e3 / (M - 1), 1)
+    new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(1, M, 3)).contiguous()
+    d2 = torch.empty(1, N, 3, device=dev)
+    i3 = torch.empty(1, N, 3, dtype=torch.int32, device=dev)
+    rec("three_nn", [1, N, M], lambda: ours.three_nn_wrapper(1, N, M, xyz, new_xyz, d2, i3), lambda: ref_cuda.three_nn_wrapper(1, N, M, xyz, new_xyz, d2, i3))
+    for ns in (16, 32):
+        radius = 1.0 if ns == 16 else 2.0
+        bidx = torch.zeros(1, M, ns, dtype=torch.int32, device=dev)
+        rec("ball_query", [1, N, M, radius, ns], lambda: ours.ball_query_wrapper(1, N, M, radius, ns, new_xyz, xyz, bidx),
+            lambda: ref_cuda.ball_query_wrapper(1, N, M, radius, ns, new_xyz, xyz, bidx))
+        for C in (64, 256):
+            if C * M * ns * 4 > 3e9:
+                continue
+            feats = torch.randn(1, C, N, device=dev)
+            out = torch.empty(1, C, M, ns, device=dev)
+            by = br.algorithmic_bytes("group_points", (1, C, N, M, ns))
+            rec("group_points", [1, C, N, M, ns], lambda: ours.group_points_wrapper(1, C, N, M, ns, feats, bidx, out),
+                lambda: ref_cuda.group_points_wrapper(1, C, N, M, ns, feats, bidx, out), by)
+            fpm = feats.transpose(1, 2).contiguous()
+            kp = (C + 6) // 4 * 4
+            opm = torch.empty(M * ns, kp, device=dev)
+            rec("group_concat_pm", [1, C, N, M, ns], lambda: ours.group_concat_pm_wrapper(1, C, N, M, ns, xyz, new_xyz, fpm, bidx, opm), None,
+                br.algorithmic_bytes("group_concat_pm", (1, C, N, M, ns, C, kp)))
+            del feats, out, fpm, opm
+    for C in (64, 256):
+        kf = torch.randn(1, C, M, device=dev)
+        w = torch.rand(1, N, 3, device=dev)
+        out = torch.empty(1, C, N, device=dev)
+        by = br.algorithmic_bytes("three_interpolate", (1, C, M, N))
+        rec("three_interpolate", [1, C, M, N], lambda: ours.three_interpolate_wrapper(1, C, M, N, kf, i3, w, out),
+            lambda: ref_cuda.three_interpolate_wrapper(1, C, M, N, kf, i3, w, out), by)
+        kpm = kf.transpose(1, 2).contiguous()
+        opm = torch.empty(N, C, device=dev)
+        rec("three_interpolate_concat_pm", [1, C, M, N], lambda: ours.three_interpolate_concat_pm_wrapper(1, C, M, N, 0, kpm, i3, w, None, opm), None, by)
+        gidx = idx
+        pts = torch.randn(1, C, N, device=dev)
+        og = torch.empty(1, C, M, device=dev)
+        rec("gather_points", [1, C, N, M], lambda: ours.gather_points_wrapper(1, C, N, M, pts, gidx, og),
+            lambda: ref_cuda.gather_points_wrapper(1, C, N, M, pts, gidx, og), br.algorithmic_bytes("gather_points", (1, C, N, M)))
+json.dump(rows, open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/op_sweep.json", "w"), indent=1)
