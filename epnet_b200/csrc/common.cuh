@@ -17,6 +17,11 @@ namespace epnet {
 
 constexpr int kSmCount = 148;  // B200
 
+// staged_rows.cu: channel-major gathers served from shared memory; kStagedNotApplicable = run the plain kernel instead
+constexpr int kStagedNotApplicable = -2;
+int launch_staged_rows(bool interp, int b, int c, int len, long long e_total, const float *src, const int *idx, const float *weight,
+                       float *out, cudaStream_t st);
+
 // Squared distance with the exact rounding sequence of the reference kernels as compiled by nvcc -O2
 // (PTX: sub,sub,mul,fma,sub,fma): d = fma(dz,dz, fma(dx,dx, dy*dy)), each difference taken as (a - b).
 // Written with intrinsics so that no compiler flag can change the contraction.

@@ -278,6 +278,8 @@ EPNET_API int epnet_three_interpolate(int b, int c, int m, int n, const float *p
     using namespace epnet;
     if (b < 0 || c < 0 || m < 0 || n < 0 || !points || !idx || !weight || !out) return EPNET_ERR_BAD_ARG;
     if (b == 0 || c == 0 || n == 0) return EPNET_OK;
+    const int staged = launch_staged_rows(true, b, c, m, n, points, idx, weight, out, (cudaStream_t)stream);
+    if (staged != kStagedNotApplicable) return staged;
     dim3 grid(((n + 3) / 4 + kIpThreads - 1) / kIpThreads, (c + kIpChannels - 1) / kIpChannels, b);
     const uintptr_t al = reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out);
     const int vec_ok = (n % 4 == 0) && ((al & 15) == 0);

@@ -101,7 +101,9 @@ def test_three_nn_bit_exact(ours, kind, n, m):
     np.testing.assert_array_equal(got_d, want_d)  # same FMA contraction -> identical bits, inf included
 
 
-@pytest.mark.parametrize("c,m,n", [(8, 64, 256), (3, 10, 17), (256, 4096, 16384), (33, 100, 1001)])
+@pytest.mark.parametrize("c,m,n", [(8, 64, 256), (3, 10, 17), (256, 4096, 16384), (33, 100, 1001),
+                                   # rows staged in shared memory: ragged last row group; one 128 KB row per CTA; partly staged 240 KB row
+                                   (70, 1024, 16384), (9, 32768, 131072), (5, 60000, 240000)])
 def test_three_interpolate(ours, c, m, n):
     rng = np.random.RandomState(41)
     pts = rng.randn(2, c, m).astype(np.float32)
@@ -118,7 +120,9 @@ def test_three_interpolate(ours, c, m, n):
 
 
 # ------------------------------------------------------------------ gather / group
-@pytest.mark.parametrize("c,n,m,ns", [(3, 100, 30, 16), (96, 4096, 1024, 32), (5, 77, 13, 3), (64, 16384, 4096, 16)])
+@pytest.mark.parametrize("c,n,m,ns", [(3, 100, 30, 16), (96, 4096, 1024, 32), (5, 77, 13, 3), (64, 16384, 4096, 16),
+                                      # staged rows: ragged row group; 160 KB rows; partly staged 256 KB rows; staged gather_points; rows too long to stage
+                                      (40, 4096, 1024, 32), (20, 40000, 4096, 32), (7, 65536, 2048, 64), (300, 1024, 4096, 16), (5, 250000, 4096, 64)])
 def test_group_and_gather(ours, c, n, m, ns):
     rng = np.random.RandomState(51)
     pts = rng.randn(2, c, n).astype(np.float32)

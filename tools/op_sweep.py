@@ -91,4 +91,13 @@ for N in (4096, 16384, 65536, 131072):
         og = torch.empty(1, C, M, device=dev)
         rec("gather_points", [1, C, N, M], lambda: ours.gather_points_wrapper(1, C, N, M, pts, gidx, og),
             lambda: ref_cuda.gather_points_wrapper(1, C, N, M, pts, gidx, og), br.algorithmic_bytes("gather_points", (1, C, N, M)))
-json.dump(rows, open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/op_sweep.json", "w"), indent=1)
+path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/op_sweep.json"
+json.dump(rows, open(path, "w"), indent=1)
+nan = float("nan")
+with open(os.path.splitext(path)[0] + ".txt", "w") as f:
+    f.write("# op-level sweep (BASELINE.json configs[4]), B=1, M=N/4; tools/op_sweep.py on one B200, CUDA events; reference kernels = "
+            "oracle/_ref (unmodified sources built for sm_100a); frac = algorithmic bytes / time / measured HBM peak\n")
+    f.write(f"{'op':28s} {'shape':34s} {'ours_us':>9s} {'ref_us':>10s} {'speedup':>8s} {'alg GB/s':>9s} {'frac':>6s}\n")
+    for r in rows:
+        f.write(f"{r['op']:28s} {str(r['shape']):34s} {r['ours_us']:9.1f} {r.get('ref_us', nan):10.1f} {r.get('speedup', nan):8.2f} "
+                f"{r.get('algorithmic_gbs', nan):9.1f} {r.get('frac_hbm', nan):6.3f}\n")
