@@ -22,6 +22,7 @@
 //     ReLU, 128-bit stores; with pool > 1 the max over `pool` consecutive rows (the nsample axis of a grouped
 //     tensor, F.max_pool2d in pointnet2_modules.py:59-61) is taken across lanes with redux.sync before storing.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace epnet {
 
@@ -103,9 +104,14 @@ struct GemmArgs {
     // k = (ky*3 + kx)*Cin + c; Cin is a power of two >= 4, so a 16-byte chunk never straddles two taps.
     int conv;              // 0: plain rows, 1: conv gather
     int H, W, cin_shift, stride, Ho, Wo;
+    // transposed convolution with kernel == stride == dk: a GEMM row is an input pixel (b, yi, xi) of an (H, W) map, column
+    // n = (ky*dk + kx)*dco + o; the epilogue writes the dco channels to output pixel (yi*dk+ky, xi*dk+kx) of the NHWC buffer y
+    // (pixel stride ldy) instead of to row-major (L, ldy).  dco % 4 == 0.
+    int dk, dco;
 };
 
-__global__ void __launch_bounds__(kGmThreads, 2)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kGmThreads, kMinBlocks)
 gemm_tf32x3_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t gm_smem[];
@@ -257,7 +263,22 @@ gemm_tf32x3_kernel(const GemmArgs a)
                 if (a.relu) f = fmaxf(f, 0.f);
                 v[j] = __float_as_uint(f);
             }
-            if (pool == 1) {
+            if (a.dk) {
+                if (row < a.L) {
+                    const int byi = row / a.W, xi = row - byi * a.W;
+                    const size_t wo = (size_t)a.W * a.dk;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int n = n0 + j;
+                        if (j < ncols && n < a.N) {
+                            const int q = n / a.dco, o = n - q * a.dco;
+                            const int ky = q / a.dk, kx = q - ky * a.dk;
+                            float *dst = a.y + (((size_t)byi * a.dk + ky) * wo + (size_t)xi * a.dk + kx) * a.ldy + o;
+                            *reinterpret_cast<uint4 *>(dst) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
+                }
+            } else if (pool == 1) {
                 if (row < a.L) {
                     float *dst = a.y + (size_t)row * a.ldy + n0;
                     if (n0 + ncols <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
@@ -360,17 +381,29 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
     if (stages < 2 && a.n_kblocks > 1) stages = 2;
     if (stages < 1) stages = 1;
     a.stages = stages;
+    int blocks = 2;
+    static const char *env = getenv("EPNET_GEMM_MINBLOCKS");
+    if (env) blocks = atoi(env);
+    if (blocks > 2) {  // more CTAs per SM: smaller stage budget
+        stages = (int)(((blocks == 3 ? 70 : 52) * 1024) / stage_bytes);
+        if (stages > kGmMaxStages) stages = kGmMaxStages;
+        if (stages > a.n_kblocks) stages = a.n_kblocks;
+        if (stages < 2 && a.n_kblocks > 1) stages = 2;
+        if (stages < 1) stages = 1;
+        a.stages = stages;
+    }
     const size_t smem = stage_bytes * stages + 1024;
     // the opt-in limit is a property of the function, not of a launch: always raise it to the hardware maximum so that a
     // kernel node captured in a CUDA graph with a large request stays launchable after later, smaller launches
+    auto kernel = blocks == 4 ? gemm_tf32x3_kernel<4> : blocks == 3 ? gemm_tf32x3_kernel<3> : gemm_tf32x3_kernel<2>;
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, gemm_tf32x3_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = (a.N + a.BN - 1) / a.BN;
     dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
-    gemm_tf32x3_kernel<<<grid, kGmThreads, smem, st>>>(a);
+    kernel<<<grid, kGmThreads, smem, st>>>(a);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 }  // namespace epnet
@@ -414,5 +447,29 @@ EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, 
     if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
     a.L = (int)rows; a.K = 9 * cin; a.N = cout; a.ldx = cin; a.ldy = ldy; a.BN = BN;
     a.relu = relu; a.pool = 1; a.x_vec_ok = 1;
+    return gemm_launch(a, (cudaStream_t)stream);
+}
+
+// Transposed convolution with kernel == stride == k (ConvTranspose2d, no overlap between patches) on an NHWC map: x rows are the
+// B*h*w input pixels (ldx floats apart, cin read), wpack packs W reordered to rows (ky, kx, o) x cin; the epilogue scatters each
+// pixel's k x k x co patch straight into out, an NHWC buffer of (B, h*k, w*k) pixels ldo floats apart (out already offset to the
+// first channel of this map's slice of a concatenation); bias (k*k*co, one value per GEMM column) or NULL.  Replaces a GEMM +
+// pixel-shuffle pass.
+EPNET_API int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                                       const float *bias, int relu, float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h <= 0 || w <= 0 || cin <= 0 || k <= 0 || co <= 0 || (co % 4) != 0 || !x || !wpack || !out || ldx < cin || ldo < co)
+        return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || (ldo % 4) != 0) return EPNET_ERR_BAD_ARG;
+    if (((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * h * w, cols = (long long)k * k * co;
+    if (rows >= (1ll << 31) || cols >= (1ll << 24)) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.x = x; a.wpack = wpack; a.bias = bias; a.y = out;
+    a.L = (int)rows; a.K = cin; a.N = (int)cols; a.ldx = ldx; a.ldy = ldo; a.BN = BN;
+    a.relu = relu; a.pool = 1; a.H = h; a.W = w; a.dk = k; a.dco = co;
+    a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
     return gemm_launch(a, (cudaStream_t)stream);
 }

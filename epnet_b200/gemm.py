@@ -59,6 +59,32 @@ class PackedLinear:
         return out
 
 
+class PackedDeconv:
+    """ConvTranspose2d with kernel == stride on NHWC activations: one GEMM per map whose epilogue writes each input pixel's
+    k x k x Cout patch into the output image (csrc/gemm_tf32x3.cu, dk mode).  weight (Cin, Cout, k, k) [+ bias (Cout)]."""
+
+    def __init__(self, weight, bias=None):
+        w = weight.detach().float()
+        self.cin, self.cout, self.k = w.shape[0], w.shape[1], w.shape[2]
+        assert w.shape[3] == self.k and self.cout % 4 == 0
+        b = None if bias is None else bias.detach().float().repeat(self.k * self.k)  # column (ky, kx, o) gets bias[o]
+        self.lin = PackedLinear(w.permute(2, 3, 1, 0).reshape(self.k * self.k * self.cout, self.cin), b)
+
+    def __call__(self, x, out, relu=False):
+        """x (B, h, w, >=Cin) NHWC (channel stride 1) -> out (B, h*k, w*k, Cout), a channel slice of an NHWC buffer"""
+        assert x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1 and x.shape[-1] >= self.cin
+        B, h, w = x.shape[:3]
+        ldx = x.stride(-2)
+        assert x.stride(-3) == w * ldx and x.stride(0) == h * w * ldx
+        ldo = out.stride(-2)
+        assert out.shape == (B, h * self.k, w * self.k, self.cout) and out.stride(-1) == 1
+        assert out.stride(-3) == w * self.k * ldo and out.stride(0) == h * self.k * w * self.k * ldo
+        lin = self.lin
+        pc._call("deconv_nhwc_tf32x3", LIB.epnet_deconv_nhwc_tf32x3, x, B, h, w, self.cin, self.k, self.cout, x.data_ptr(), ldx,
+                 lin.wpack.data_ptr(), lin.BN, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(), ldo)
+        return out
+
+
 class PackedConv3x3:
     """3x3 / pad 1 convolution on NHWC activations as an implicit GEMM (csrc/gemm_tf32x3.cu, conv mode).
     weight (Cout, Cin, 3, 3) [+ bias]; Cin is zero-padded to a power of two >= 4 (the 3-channel input image becomes 4)."""

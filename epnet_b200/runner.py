@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
-from .gemm import PackedConv3x3, PackedLinear
+from .gemm import PackedConv3x3, PackedDeconv, PackedLinear
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -234,11 +234,9 @@ class BackboneRunner:
                 self._img_channels = img_channels
                 cat = torch.empty((B, H, W, self.deconv_cat_width), **f32)
                 col = 0
-                for i, (lin, k, co) in enumerate(self.deconv_pm):
-                    hi, wi, ci = imgs[i].shape[1], imgs[i].shape[2], img_channels[i]
-                    y = lin(imgs[i].view(-1, imgs[i].shape[3])[:, :ci], relu=False)  # (B*hi*wi, k*k*co): each input pixel's k x k patch
-                    pc.deconv_shuffle_nhwc_wrapper(B, hi, wi, k, co, y, cat, col)
-                    col += co
+                for i, de in enumerate(self.deconv_pm):  # each input pixel's k x k patch goes straight into its slice of the concat
+                    de(imgs[i], cat[..., col:col + de.cout])
+                    col += de.cout
                 img_fusion = self.img_fuse_pm(cat.view(-1, self.deconv_cat_width), relu=True).view(B, H, W, -1)
                 img_fusion_done = torch.cuda.Event()
                 img_fusion_done.record(self.s_img)
@@ -339,11 +337,10 @@ class BackboneRunner:
             self.deconv_pm, biases = [], []
             for de in self.model.DeConv:  # ConvTranspose2d weight: (Cin, Cout, k, k), kernel == stride
                 k, co = de.kernel_size[0], de.out_channels
-                assert de.stride[0] == k and de.kernel_size[1] == k
-                wd = de.weight.detach().permute(2, 3, 1, 0).reshape(k * k * co, de.in_channels)  # row (ky, kx, o)
-                self.deconv_pm.append((PackedLinear(wd, None), k, co))
-                biases.append(de.bias.detach() if de.bias is not None else torch.zeros(co, device=wd.device))
-            self.deconv_cat_width = sum(co for _, _, co in self.deconv_pm)
+                assert de.stride[0] == k and de.kernel_size[1] == k and de.stride[1] == k
+                self.deconv_pm.append(PackedDeconv(de.weight, None))
+                biases.append(de.bias.detach() if de.bias is not None else torch.zeros(co, device=de.weight.device))
+            self.deconv_cat_width = sum(de.cout for de in self.deconv_pm)
             fc, fbn = self.model.image_fusion_conv, self.model.image_fusion_bn
             wq = fc.weight.detach().flatten(1)
             # the transposed convolutions' biases pass linearly through the 1x1 fusion conv: fold them into its bias

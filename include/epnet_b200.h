@@ -147,6 +147,13 @@ int epnet_grid_gather_nhwc_pm(int b, int c, int h, int w, int n, const float *fm
                               float *out, int ldo, void *stream);
 int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, const float *y, float *out, int ldo, int col_off, void *stream);
 
+/* ConvTranspose2d with kernel == stride == k (lib/net/pointnet2_msg.py:170-172 builds them that way) on an NHWC map as one
+ * tcgen05 GEMM whose epilogue scatters every input pixel's k x k x co patch into the NHWC output (pixels ldo floats apart, `out`
+ * pre-offset to this map's channel slice of the concatenation at pointnet2_msg.py:242).  x: B*h*w rows ldx apart, cin read;
+ * wpack: rows ordered (ky, kx, o); bias: k*k*co values or NULL. */
+int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                             const float *bias, int relu, float *out, int ldo, void *stream);
+
 /* ---- next row of the scope table: 3D RoI point pooling ------------------------------------------------------------ */
 
 /* replaces roipool3dLauncher (/root/reference/lib/utils/roipool3d/src/roipool3d.cpp:8-9, roipool3d_kernel.cu:207-236), same

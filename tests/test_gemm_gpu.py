@@ -80,3 +80,22 @@ def test_conv3x3_nhwc_matches_fp64(B, H, W, cin, cout, stride, relu):
     scale = want.abs().max().item()
     print("conv %dx%d cin=%d cout=%d s%d: max abs err %.3e, scale %.3e, rel %.2e" % (H, W, cin, cout, stride, err, scale, err / scale))
     assert err <= 1e-5 * scale  # K = 9*Cin up to 4608: the tensor core's truncating accumulate shows (~2e-9 per k)
+
+
+@pytest.mark.parametrize("B,h,w,cin,cpad,k,co", [(2, 6, 10, 64, 64, 2, 16), (1, 5, 7, 24, 32, 4, 16), (2, 3, 5, 512, 512, 16, 16), (1, 7, 3, 40, 40, 3, 8)])
+def test_deconv_nhwc_matches_fp64(B, h, w, cin, cpad, k, co):
+    """ConvTranspose2d(kernel == stride) as one GEMM with a scattering epilogue, written into a slice of a wider NHWC buffer."""
+    from epnet_b200.gemm import PackedDeconv
+    g = torch.Generator(device="cpu").manual_seed(h * w + cin + k)
+    x = torch.randn(B, cin, h, w, generator=g).cuda()
+    wt = (torch.randn(cin, co, k, k, generator=g) / cin ** 0.5).cuda()
+    b = torch.randn(co, generator=g).cuda()
+    x_nhwc = torch.zeros(B, h, w, cpad, device="cuda")
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1)
+    cat = torch.full((B, h * k, w * k, co + 24), 7.0, device="cuda")
+    PackedDeconv(wt, b)(x_nhwc, cat[..., 8:8 + co])
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv_transpose2d(x.double(), wt.double(), b.double(), stride=k).permute(0, 2, 3, 1)
+    err = (cat[..., 8:8 + co].double() - want).abs().max().item()
+    assert err <= 4e-6 * want.abs().max().item()
+    assert (cat[..., :8] == 7.0).all() and (cat[..., 8 + co:] == 7.0).all()  # neighbours of the slice untouched
