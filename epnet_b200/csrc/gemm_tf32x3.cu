@@ -22,7 +22,6 @@
 //     ReLU, 128-bit stores; with pool > 1 the max over `pool` consecutive rows (the nsample axis of a grouped
 //     tensor, F.max_pool2d in pointnet2_modules.py:59-61) is taken across lanes with redux.sync before storing.
 #include "common.cuh"
-#include <cstdlib>
 
 namespace epnet {
 
@@ -110,8 +109,7 @@ struct GemmArgs {
     int dk, dco;
 };
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kGmThreads, kMinBlocks)
+__global__ void __launch_bounds__(kGmThreads, 2)
 gemm_tf32x3_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t gm_smem[];
@@ -129,10 +127,11 @@ gemm_tf32x3_kernel(const GemmArgs a)
     // stage layout: [A_hi | A_lo | B_hi | B_lo], every plane 1024-byte aligned (BN % 8 == 0)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
 
-    // two fp32 accumulators: columns [0,BN) take hi*hi, columns [BNP, BNP+BN) take the two correction terms.  The tensor
+    // two fp32 accumulators: columns [0,BN) take hi*hi, columns [corr_off, corr_off+BN) take the two correction terms.  The tensor
     // core's accumulate truncates, so its error grows with the number of read-modify-writes; keeping the small terms apart
     // leaves the main accumulator with K/8 updates instead of 3K/8 and the sum is formed once, in fp32 RN, in the epilogue.
     const uint32_t BNP = (uint32_t)((BN + 31) & ~31);
+    const uint32_t corr_off = BN <= 128 ? (uint32_t)BN : BNP;  // see the MMA issuer
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2 * BNP) tmem_cols <<= 1;
 
@@ -164,46 +163,59 @@ gemm_tf32x3_kernel(const GemmArgs a)
         const int chunk = tid & 7;          // 16-byte chunk of the 128-byte k-row
         const int rbase = tid >> 3;         // 0..15; rows rbase + 16*i
         // global loads of k-block kb+1 are issued before k-block kb is converted and stored: one block of latency is hidden
-        // conv mode: (b, yo, xo) of this thread's 8 rows, packed; -1 marks rows past the end
-        int pix_base[8], pix_yx[8];
+        // per row, computed once: plain rows -> pointer to the row, mask = row exists; conv -> pointer to the top-left tap
+        // (dy = dx = -1; only dereferenced where the mask allows) and a 9-bit mask of the taps that fall inside the image.
+        // Per k-block only a thread-uniform offset is added, so the k loop carries no per-row index arithmetic.
+        const float *rowp[8];
+        uint32_t rmask[8];
         if (a.conv) {
+            int row = row0 + rbase;
+            int b = row / (a.Ho * a.Wo);
+            const int rem = row - b * (a.Ho * a.Wo);
+            int yo = rem / a.Wo, xo = rem - yo * a.Wo;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int y0 = yo * a.stride - 1, x0 = xo * a.stride - 1;
+                uint32_t vy = 0, vx = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    vy |= (uint32_t)(y0 + d >= 0 && y0 + d < a.H) << d;
+                    vx |= (uint32_t)(x0 + d >= 0 && x0 + d < a.W) << d;
+                }
+                const uint32_t m = ((vy & 1u) ? vx : 0u) | ((vy & 2u) ? vx << 3 : 0u) | ((vy & 4u) ? vx << 6 : 0u);
+                rmask[i] = row < a.L ? m : 0u;
+                rowp[i] = a.x + (((long long)(b * a.H + y0) * a.W + x0) << a.cin_shift);
+                row += 16;  // next row of this thread: 16 output pixels further along the scan
+                xo += 16;
+                while (xo >= a.Wo) { xo -= a.Wo; ++yo; }
+                while (yo >= a.Ho) { yo -= a.Ho; ++b; }
+            }
+        } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = row0 + rbase + 16 * i;
-                if (row < a.L) {
-                    const int b = row / (a.Ho * a.Wo);
-                    const int rem = row - b * (a.Ho * a.Wo);
-                    const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
-                    pix_base[i] = b * a.H;                                   // image row base of the scene
-                    pix_yx[i] = ((yo * a.stride - 1) << 16) | ((xo * a.stride - 1) & 0xffff);  // top-left tap, 16-bit signed each
-                } else {
-                    pix_base[i] = -1;
-                    pix_yx[i] = 0;
-                }
+                rmask[i] = row < a.L ? 1u : 0u;
+                rowp[i] = a.x + (size_t)row * a.ldx;
             }
         }
         auto load_block = [&](int kb, float4 (&v)[8]) {
             const int k0 = kb * kGmBK + chunk * 4;
             if (a.conv) {
                 const int tap = k0 >> a.cin_shift;            // (ky*3 + kx); >= 9 in the zero padding of the last k-block
-                const int c = k0 & ((1 << a.cin_shift) - 1);
                 const int ky = tap / 3, kx = tap - 3 * ky;
+                const int off = ((ky * a.W + kx) << a.cin_shift) + (k0 & ((1 << a.cin_shift) - 1));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int yi = (pix_yx[i] >> 16) + ky;
-                    const int xi = (int)(short)(pix_yx[i] & 0xffff) + kx;
-                    if (pix_base[i] >= 0 && tap < 9 && yi >= 0 && yi < a.H && xi >= 0 && xi < a.W)
-                        v[i] = __ldg(reinterpret_cast<const float4 *>(a.x + ((((size_t)(pix_base[i] + yi)) * a.W + xi) << a.cin_shift) + c));
+                    if ((rmask[i] >> tap) & 1u) v[i] = __ldg(reinterpret_cast<const float4 *>(rowp[i] + off));
                 }
                 return;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int row = row0 + rbase + 16 * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < a.L && k0 < a.K) {
-                    const float *src = a.x + (size_t)row * a.ldx + k0;
+                if (rmask[i] && k0 < a.K) {
+                    const float *src = rowp[i] + k0;
                     if (a.x_vec_ok && k0 + 4 <= a.K) {
                         v[i] = __ldg(reinterpret_cast<const float4 *>(src));
                     } else {
@@ -215,32 +227,37 @@ gemm_tf32x3_kernel(const GemmArgs a)
                 }
             }
         };
+        uint32_t slot[8];  // byte offset of this thread's chunk of row rbase + 16*i inside a plane (swizzled)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rbase + 16 * i;
+            slot[i] = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+        }
         float4 cur[8], nxt[8];
         load_block(0, cur);
+        int s = 0;
+        uint32_t ph = 0;
         for (int kb = 0; kb < a.n_kblocks; ++kb) {
-            const int s = kb % a.stages;
-            const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
             if (kb + 1 < a.n_kblocks) load_block(kb + 1, nxt);
             mbar_wait(&empty[s], ph ^ 1u);
             uint8_t *a_hi = smem + (size_t)s * stage_bytes;
             uint8_t *a_lo = a_hi + a_bytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
                 const float4 v = cur[i];
                 uint4 hi, lo;
                 hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
                 hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
                 lo.x = __float_as_uint(__fsub_rn(v.x, __uint_as_float(hi.x))); lo.y = __float_as_uint(__fsub_rn(v.y, __uint_as_float(hi.y)));
                 lo.z = __float_as_uint(__fsub_rn(v.z, __uint_as_float(hi.z))); lo.w = __float_as_uint(__fsub_rn(v.w, __uint_as_float(hi.w)));
-                const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                *reinterpret_cast<uint4 *>(a_hi + slot[i]) = hi;
+                *reinterpret_cast<uint4 *>(a_lo + slot[i]) = lo;
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(&full_a[s]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
 
         // ===================== epilogue =====================
@@ -253,7 +270,7 @@ gemm_tf32x3_kernel(const GemmArgs a)
             uint32_t v[32], w[32];
             const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
             tmem_ld32(taddr, v);
-            tmem_ld32(taddr + BNP, w);
+            tmem_ld32(taddr + corr_off, w);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int ncols = min(32, BN - c0);
             const int n0 = ntile * BN + c0;
@@ -324,10 +341,16 @@ gemm_tf32x3_kernel(const GemmArgs a)
     } else if (warp == 4) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
+            // BN <= 128: the two weight planes are adjacent in the stage ([B_hi | B_lo], 8-row atoms), so ONE MMA with N = 2*BN forms
+            // hi*hi into columns [0,BN) and hi*lo into [BN,2BN) while reading A_hi once; lo*hi then accumulates onto [BN,2BN).
+            // Shared-memory operand reads per k-step drop from 3 to 2 A-planes (the kernel is shared-memory-bandwidth bound
+            // for small N).  BN > 128 keeps three MMAs (N = 2*BN would exceed 256).
+            const bool fused_b = BN <= 128;
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                const int s = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
                 mbar_wait(&full_a[s], ph);
                 mbar_wait(&full_b[s], ph);
                 tc_fence_after();
@@ -337,11 +360,17 @@ gemm_tf32x3_kernel(const GemmArgs a)
 #pragma unroll
                 for (int ks = 0; ks < kGmBK / 8; ++ks) {
                     const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along the swizzled row
-                    umma_tf32(tmem_acc + BNP, d_al + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
-                    umma_tf32(tmem_acc + BNP, d_ah + adv, d_bl + adv, idesc, 1u);
-                    umma_tf32(tmem_acc, d_ah + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
+                    if (fused_b) {
+                        umma_tf32(tmem_acc, d_ah + adv, d_bh + adv, idesc2, (kb | ks) ? 1u : 0u);
+                        umma_tf32(tmem_acc + corr_off, d_al + adv, d_bh + adv, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_acc + corr_off, d_al + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
+                        umma_tf32(tmem_acc + corr_off, d_ah + adv, d_bl + adv, idesc, 1u);
+                        umma_tf32(tmem_acc, d_ah + adv, d_bh + adv, idesc, (kb | ks) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(&accum_bar);
         }
@@ -350,12 +379,13 @@ gemm_tf32x3_kernel(const GemmArgs a)
         // ===================== weight loader (one thread) =====================
         if (lane == 0) {
             const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                const int s = kb % a.stages;
-                const uint32_t ph = (uint32_t)(kb / a.stages) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
                 bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full_b[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
@@ -381,21 +411,10 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
     if (stages < 2 && a.n_kblocks > 1) stages = 2;
     if (stages < 1) stages = 1;
     a.stages = stages;
-    int blocks = 2;
-    static const char *env = getenv("EPNET_GEMM_MINBLOCKS");
-    if (env) blocks = atoi(env);
-    if (blocks > 2) {  // more CTAs per SM: smaller stage budget
-        stages = (int)(((blocks == 3 ? 70 : 52) * 1024) / stage_bytes);
-        if (stages > kGmMaxStages) stages = kGmMaxStages;
-        if (stages > a.n_kblocks) stages = a.n_kblocks;
-        if (stages < 2 && a.n_kblocks > 1) stages = 2;
-        if (stages < 1) stages = 1;
-        a.stages = stages;
-    }
     const size_t smem = stage_bytes * stages + 1024;
     // the opt-in limit is a property of the function, not of a launch: always raise it to the hardware maximum so that a
     // kernel node captured in a CUDA graph with a large request stays launchable after later, smaller launches
-    auto kernel = blocks == 4 ? gemm_tf32x3_kernel<4> : blocks == 3 ? gemm_tf32x3_kernel<3> : gemm_tf32x3_kernel<2>;
+    auto kernel = gemm_tf32x3_kernel;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
     if (e != cudaSuccess) return (int)e;
