@@ -98,6 +98,7 @@ struct GemmArgs {
     int relu;
     int pool;              // 1, or the number of consecutive rows pooled by max: 2, 4, 8, 16 or 32
     int stages;
+    int depth;             // A-from-TMEM kernel: k-blocks of X in flight per warp (cp.async ring slots)
     int x_vec_ok;          // x base 16-byte aligned and ldx % 4 == 0
     // implicit 3x3 convolution (pad 1): x is an NHWC image (B, H, W, Cin), a GEMM row is an output pixel (b, yo, xo),
     // k = (ky*3 + kx)*Cin + c; Cin is a power of two >= 4, so a 16-byte chunk never straddles two taps.
@@ -108,6 +109,202 @@ struct GemmArgs {
     // (pixel stride ldy) instead of to row-major (L, ldy).  dco % 4 == 0.
     int dk, dco;
 };
+
+// 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
+__device__ __forceinline__ void cp_async16_cg(void *dst_smem, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void *dst_smem, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// The 8 rows of X a producer thread serves (first, first + step, ...), resolved once per tile: plain rows -> pointer to the row,
+// mask = row exists; conv -> pointer to the top-left tap (dy = dx = -1; only dereferenced where the mask allows) and a 9-bit
+// mask of the taps that fall inside the image.  Per k-block only a thread-uniform offset is added, so the k loop carries no
+// per-row index arithmetic.
+struct RowSource {
+    const float *rowp[8];
+    uint32_t rmask[8];
+
+    __device__ __forceinline__ void init(const GemmArgs &a, int first, int step)
+    {
+        if (a.conv) {
+            int row = first;
+            int b = row / (a.Ho * a.Wo);
+            const int rem = row - b * (a.Ho * a.Wo);
+            int yo = rem / a.Wo, xo = rem - yo * a.Wo;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int y0 = yo * a.stride - 1, x0 = xo * a.stride - 1;
+                uint32_t vy = 0, vx = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    vy |= (uint32_t)(y0 + d >= 0 && y0 + d < a.H) << d;
+                    vx |= (uint32_t)(x0 + d >= 0 && x0 + d < a.W) << d;
+                }
+                const uint32_t m = ((vy & 1u) ? vx : 0u) | ((vy & 2u) ? vx << 3 : 0u) | ((vy & 4u) ? vx << 6 : 0u);
+                rmask[i] = row < a.L ? m : 0u;
+                rowp[i] = a.x + (((long long)(b * a.H + y0) * a.W + x0) << a.cin_shift);
+                row += step;  // the next row of this thread is `step` output pixels further along the scan
+                xo += step;
+                while (xo >= a.Wo) { xo -= a.Wo; ++yo; }
+                while (yo >= a.Ho) { yo -= a.Ho; ++b; }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = first + step * i;
+                rmask[i] = row < a.L ? 1u : 0u;
+                rowp[i] = a.x + (size_t)row * a.ldx;
+            }
+        }
+    }
+
+    // this thread's 16-byte chunk (4 floats from column k0) of each of its rows; zeros where nothing exists
+    __device__ __forceinline__ void load(const GemmArgs &a, int k0, float4 (&v)[8]) const
+    {
+        if (a.conv) {
+            const int tap = k0 >> a.cin_shift;            // (ky*3 + kx); >= 9 in the zero padding of the last k-block
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const int off = ((ky * a.W + kx) << a.cin_shift) + (k0 & ((1 << a.cin_shift) - 1));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((rmask[i] >> tap) & 1u) v[i] = __ldg(reinterpret_cast<const float4 *>(rowp[i] + off));
+            }
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rmask[i] && k0 < a.K) {
+                const float *src = rowp[i] + k0;
+                if (a.x_vec_ok && k0 + 4 <= a.K) {
+                    v[i] = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    v[i].x = __ldg(src + 0);
+                    if (k0 + 1 < a.K) v[i].y = __ldg(src + 1);
+                    if (k0 + 2 < a.K) v[i].z = __ldg(src + 2);
+                    if (k0 + 3 < a.K) v[i].w = __ldg(src + 3);
+                }
+            }
+        }
+    }
+
+    // the same chunks, copied asynchronously to base + dst_off[i] (cp.async group of the caller); rows whose base or stride
+    // is not 16-byte aligned are loaded and stored synchronously instead
+    __device__ __forceinline__ void copy_async(const GemmArgs &a, int k0, uint8_t *base, const uint32_t (&dst_off)[8]) const
+    {
+        if (a.conv) {
+            const int tap = k0 >> a.cin_shift;
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const int off = ((ky * a.W + kx) << a.cin_shift) + (k0 & ((1 << a.cin_shift) - 1));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = (rmask[i] >> tap) & 1u;
+                cp_async16_ca(base + dst_off[i], ok ? rowp[i] + off : a.x, ok ? 16u : 0u);  // neighbouring pixels share taps: keep L1
+            }
+            return;
+        }
+        if (a.x_vec_ok) {
+            const int valid = min(4, a.K - k0);  // floats of this chunk inside K (<= 0: none)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = rmask[i] && valid > 0;
+                cp_async16_cg(base + dst_off[i], ok ? rowp[i] + k0 : a.x, ok ? (uint32_t)valid * 4u : 0u);
+            }
+            return;
+        }
+        float4 v[8];
+        load(a, k0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4 *>(base + dst_off[i]) = v[i];
+    }
+};
+
+// Accumulator -> global memory: main + correction, bias, ReLU, then plain rows / pooled rows / the transposed convolution's
+// patch scatter.  Called by the four warps whose warp index selects the TMEM lane quarter (thread = lane = tile row).
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_acc, uint32_t corr_off, int warp, int lane, int row0,
+                                              int ntile, const float *bias_s)
+{
+    const int BN = a.BN;
+    const int r = warp * 32 + lane;  // TMEM lane == tile row
+    const int row = row0 + r;
+    const int pool = a.pool;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32], w[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + corr_off, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int ncols = min(32, BN - c0);
+        const int n0 = ntile * BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) + bias_s[c0 + j];
+            if (a.relu) f = fmaxf(f, 0.f);
+            v[j] = __float_as_uint(f);
+        }
+        if (a.dk) {
+            if (row < a.L) {
+                const int byi = row / a.W, xi = row - byi * a.W;
+                const size_t wo = (size_t)a.W * a.dk;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + j;
+                    if (j < ncols && n < a.N) {
+                        const int q = n / a.dco, o = n - q * a.dco;
+                        const int ky = q / a.dk, kx = q - ky * a.dk;
+                        float *dst = a.y + (((size_t)byi * a.dk + ky) * wo + (size_t)xi * a.dk + kx) * a.ldy + o;
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+        } else if (pool == 1) {
+            if (row < a.L) {
+                float *dst = a.y + (size_t)row * a.ldy + n0;
+                if (n0 + ncols <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < ncols) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols && n0 + j < a.N) dst[j] = __uint_as_float(v[j]);
+                }
+            }
+        } else {
+            // max over `pool` consecutive rows (= lanes): order-preserving float->uint map, then an xor-butterfly inside
+            // aligned groups of `pool` lanes; each step runs over all 32 columns (independent shuffles in flight)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t u = row < a.L ? v[j] : 0xff800000u;  // -inf for rows past the end
+                v[j] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                if (d < pool) {  // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], d));
+                }
+            }
+            // every lane of a group now holds the group's maxima; lane t of the group stores columns j == t (mod pool)
+            if (row < a.L) {
+                float *dst = a.y + (size_t)(row / pool) * a.ldy + n0;
+                const int t = lane % pool;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if ((j % pool) == t && j < ncols && n0 + j < a.N) {
+                        const uint32_t u = v[j];
+                        dst[j] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+                    }
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kGmThreads, 2)
 gemm_tf32x3_kernel(const GemmArgs a)
@@ -163,70 +360,9 @@ gemm_tf32x3_kernel(const GemmArgs a)
         const int chunk = tid & 7;          // 16-byte chunk of the 128-byte k-row
         const int rbase = tid >> 3;         // 0..15; rows rbase + 16*i
         // global loads of k-block kb+1 are issued before k-block kb is converted and stored: one block of latency is hidden
-        // per row, computed once: plain rows -> pointer to the row, mask = row exists; conv -> pointer to the top-left tap
-        // (dy = dx = -1; only dereferenced where the mask allows) and a 9-bit mask of the taps that fall inside the image.
-        // Per k-block only a thread-uniform offset is added, so the k loop carries no per-row index arithmetic.
-        const float *rowp[8];
-        uint32_t rmask[8];
-        if (a.conv) {
-            int row = row0 + rbase;
-            int b = row / (a.Ho * a.Wo);
-            const int rem = row - b * (a.Ho * a.Wo);
-            int yo = rem / a.Wo, xo = rem - yo * a.Wo;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int y0 = yo * a.stride - 1, x0 = xo * a.stride - 1;
-                uint32_t vy = 0, vx = 0;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    vy |= (uint32_t)(y0 + d >= 0 && y0 + d < a.H) << d;
-                    vx |= (uint32_t)(x0 + d >= 0 && x0 + d < a.W) << d;
-                }
-                const uint32_t m = ((vy & 1u) ? vx : 0u) | ((vy & 2u) ? vx << 3 : 0u) | ((vy & 4u) ? vx << 6 : 0u);
-                rmask[i] = row < a.L ? m : 0u;
-                rowp[i] = a.x + (((long long)(b * a.H + y0) * a.W + x0) << a.cin_shift);
-                row += 16;  // next row of this thread: 16 output pixels further along the scan
-                xo += 16;
-                while (xo >= a.Wo) { xo -= a.Wo; ++yo; }
-                while (yo >= a.Ho) { yo -= a.Ho; ++b; }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = row0 + rbase + 16 * i;
-                rmask[i] = row < a.L ? 1u : 0u;
-                rowp[i] = a.x + (size_t)row * a.ldx;
-            }
-        }
-        auto load_block = [&](int kb, float4 (&v)[8]) {
-            const int k0 = kb * kGmBK + chunk * 4;
-            if (a.conv) {
-                const int tap = k0 >> a.cin_shift;            // (ky*3 + kx); >= 9 in the zero padding of the last k-block
-                const int ky = tap / 3, kx = tap - 3 * ky;
-                const int off = ((ky * a.W + kx) << a.cin_shift) + (k0 & ((1 << a.cin_shift) - 1));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((rmask[i] >> tap) & 1u) v[i] = __ldg(reinterpret_cast<const float4 *>(rowp[i] + off));
-                }
-                return;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rmask[i] && k0 < a.K) {
-                    const float *src = rowp[i] + k0;
-                    if (a.x_vec_ok && k0 + 4 <= a.K) {
-                        v[i] = __ldg(reinterpret_cast<const float4 *>(src));
-                    } else {
-                        v[i].x = __ldg(src + 0);
-                        if (k0 + 1 < a.K) v[i].y = __ldg(src + 1);
-                        if (k0 + 2 < a.K) v[i].z = __ldg(src + 2);
-                        if (k0 + 3 < a.K) v[i].w = __ldg(src + 3);
-                    }
-                }
-            }
-        };
+        RowSource src;
+        src.init(a, row0 + rbase, 16);
+        auto load_block = [&](int kb, float4 (&v)[8]) { src.load(a, kb * kGmBK + chunk * 4, v); };
         uint32_t slot[8];  // byte offset of this thread's chunk of row rbase + 16*i inside a plane (swizzled)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -263,80 +399,7 @@ gemm_tf32x3_kernel(const GemmArgs a)
         // ===================== epilogue =====================
         mbar_wait(&accum_bar, 0u);
         tc_fence_after();
-        const int r = warp * 32 + lane;  // TMEM lane == tile row
-        const int row = row0 + r;
-        const int pool = a.pool;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32], w[32];
-            const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-            tmem_ld32(taddr, v);
-            tmem_ld32(taddr + corr_off, w);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int ncols = min(32, BN - c0);
-            const int n0 = ntile * BN + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) + bias_s[c0 + j];
-                if (a.relu) f = fmaxf(f, 0.f);
-                v[j] = __float_as_uint(f);
-            }
-            if (a.dk) {
-                if (row < a.L) {
-                    const int byi = row / a.W, xi = row - byi * a.W;
-                    const size_t wo = (size_t)a.W * a.dk;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int n = n0 + j;
-                        if (j < ncols && n < a.N) {
-                            const int q = n / a.dco, o = n - q * a.dco;
-                            const int ky = q / a.dk, kx = q - ky * a.dk;
-                            float *dst = a.y + (((size_t)byi * a.dk + ky) * wo + (size_t)xi * a.dk + kx) * a.ldy + o;
-                            *reinterpret_cast<uint4 *>(dst) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
-                    }
-                }
-            } else if (pool == 1) {
-                if (row < a.L) {
-                    float *dst = a.y + (size_t)row * a.ldy + n0;
-                    if (n0 + ncols <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (j < ncols) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols && n0 + j < a.N) dst[j] = __uint_as_float(v[j]);
-                    }
-                }
-            } else {
-                // max over `pool` consecutive rows (= lanes): order-preserving float->uint map, then an xor-butterfly inside
-                // aligned groups of `pool` lanes; each step runs over all 32 columns (independent shuffles in flight)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t u = row < a.L ? v[j] : 0xff800000u;  // -inf for rows past the end
-                    v[j] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-                }
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    if (d < pool) {  // warp-uniform
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], d));
-                    }
-                }
-                // every lane of a group now holds the group's maxima; lane t of the group stores columns j == t (mod pool)
-                if (row < a.L) {
-                    float *dst = a.y + (size_t)(row / pool) * a.ldy + n0;
-                    const int t = lane % pool;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if ((j % pool) == t && j < ncols && n0 + j < a.N) {
-                            const uint32_t u = v[j];
-                            dst[j] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-                        }
-                    }
-                }
-            }
-        }
+        gemm_epilogue(a, tmem_acc, corr_off, warp, lane, row0, ntile, bias_s);
         tc_fence_before();
     } else if (warp == 4) {
         // ===================== MMA issuer (one thread) =====================
@@ -398,12 +461,230 @@ gemm_tf32x3_kernel(const GemmArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// A-from-TMEM variant for narrow tiles (BN <= 64).  With few output columns the SS kernel above is bound by shared-memory
+// bandwidth: per k-block it writes 32 KB of X planes and the tensor core reads them back twice.  Here X never becomes a
+// shared-memory operand: a producer warp copies its 32 rows into a warp-private ring with cp.async (coalesced: 8 lanes per
+// 128-byte row segment, several k-blocks ahead), reads them back turned so that lane l holds row l, and writes hi (the raw fp32 words: kind::tf32 ignores the 13 low mantissa
+// bits, so they ARE x & 0xffffe000) and lo = x - hi into TMEM columns with tcgen05.st; the MMAs take A from TMEM
+// (tcgen05.mma [d], [a], b-desc).  Shared memory then carries only the weights (ring of k-blocks).
+//
+// TMEM columns (256 per CTA, two CTAs per SM): [0, 2*BN) accumulators (main | correction), then a_stages x 64 columns of X
+// (hi 32 | lo 32), a_stages = 2 or 3.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, single CTA.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+constexpr int kTsMaxBStages = 3;
+constexpr int kTsMaxAStages = 3;
+
+__global__ void __launch_bounds__(kGmThreads, 2)
+gemm_tf32x3_ts_kernel(const GemmArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t gm_smem[];
+    __shared__ __align__(8) uint64_t full_a[kTsMaxAStages], empty_a[kTsMaxAStages], full_b[kTsMaxBStages], empty_b[kTsMaxBStages], accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float bias_s[256 + 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * kGmBM;
+    const int ntile = blockIdx.y;
+    const int BN = a.BN;                           // <= 64
+    const uint32_t b_bytes = (uint32_t)BN * 128;   // one plane of the W tile
+    // shared memory: [4 warps x depth x 4 KB of fp32 rows | ring of a.stages x (B_hi | B_lo)]
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
+    uint8_t *b_ring = smem + (size_t)4 * a.depth * 4096;
+
+    const uint32_t acc_cols = (uint32_t)((2 * BN + 31) & ~31);
+    const int a_stages = (256 - (int)acc_cols) / 64 > kTsMaxAStages ? kTsMaxAStages : (256 - (int)acc_cols) / 64;  // 2 (BN = 64) or 3
+    const uint32_t tmem_cols = 256;
+    const uint32_t corr_off = (uint32_t)BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < a_stages; ++s) {
+            mbar_init(&full_a[s], kGmProducers);
+            mbar_init(&empty_a[s], 1);
+        }
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = tid; j < 256 + 32; j += kGmThreads) {
+        const int n = ntile * BN + j;
+        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+    const uint32_t tmem_a0 = tmem_acc + acc_cols;  // first X stage
+
+    if (warp < 4) {
+        // ===================== X producers =====================
+        const int chunk = lane & 7;   // 16-byte chunk of the 128-byte k-row
+        const int rsub = lane >> 3;   // loads: rows 32*warp + 4*i + rsub (i < 8), i.e. the warp's own TMEM lane quarter
+        RowSource src;
+        src.init(a, row0 + 32 * warp + rsub, 4);
+        // warp-private ring of `depth` slots of 32 rows x 128 B (chunk c of row r at c ^ (r & 7)): k-blocks are copied in with
+        // cp.async `depth` ahead (no register staging, no cross-warp synchronisation), then each lane reads back its own row
+        uint8_t *ring = smem + (size_t)warp * a.depth * 4096;
+        uint32_t st_off[8], ld_off[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsub;
+            st_off[i] = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+            ld_off[i] = (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4);  // chunk i of this lane's row
+        }
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int j = 0; j < a.depth; ++j) {  // always `depth` groups, empty ones past the end: group index == k-block index
+            if (j < a.n_kblocks) src.copy_async(a, j * kGmBK + chunk * 4, ring + j * 4096, st_off);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        int t = 0, slot = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            // k-block kb has landed when at most depth-1 newer groups are pending
+            if (a.depth == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            else if (a.depth == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else if (a.depth == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else asm volatile("cp.async.wait_group 3;" ::: "memory");
+            __syncwarp();  // every lane's copies of this k-block are complete and visible to the warp
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(ring + slot * 4096 + ld_off[i]);
+                v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+            }
+            __syncwarp();  // the slot has been read by all lanes: refill it
+            if (kb + a.depth < a.n_kblocks) src.copy_async(a, (kb + a.depth) * kGmBK + chunk * 4, ring + slot * 4096, st_off);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            mbar_wait(&empty_a[t], ph ^ 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_a0 + (uint32_t)t * 64u + lane_addr;
+            tmem_st32(taddr, v);  // hi: the raw words
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = __uint_as_float(v[j]);
+                v[j] = __float_as_uint(__fsub_rn(x, __uint_as_float(v[j] & 0xffffe000u)));
+            }
+            tmem_st32(taddr + 32u, v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&full_a[t]);
+            if (++t == a_stages) { t = 0; ph ^= 1u; }
+            if (++slot == a.depth) slot = 0;
+        }
+
+        // ===================== epilogue =====================
+        mbar_wait(&accum_bar, 0u);
+        tc_fence_after();
+        gemm_epilogue(a, tmem_acc, corr_off, warp, lane, row0, ntile, bias_s);
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            int t = 0, s = 0;
+            uint32_t pha = 0, phb = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&full_a[t], pha);
+                mbar_wait(&full_b[s], phb);
+                tc_fence_after();
+                const uint64_t d_bh = umma_desc_k_sw128(smem_u32(b_ring + (size_t)s * 2 * b_bytes));  // [B_hi | B_lo]: 2*BN rows
+                const uint32_t a_hi = tmem_a0 + (uint32_t)t * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int ks = 0; ks < kGmBK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along the swizzled row
+                    umma_tf32_ts(tmem_acc, a_hi + ks * 8, d_bh + adv, idesc2, (kb | ks) ? 1u : 0u);  // hi*hi | hi*lo
+                    umma_tf32_ts(tmem_acc + corr_off, a_lo + ks * 8, d_bh + adv, idesc, 1u);           // lo*hi
+                }
+                umma_commit(&empty_a[t]);
+                umma_commit(&empty_b[s]);
+                if (++t == a_stages) { t = 0; pha ^= 1u; }
+                if (++s == a.stages) { s = 0; phb ^= 1u; }
+            }
+            umma_commit(&accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ===================== weight loader (one thread) =====================
+        if (lane == 0) {
+            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&empty_b[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
+                bulk_g2s(b_ring + (size_t)s * 2 * b_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full_b[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
 }  // namespace epnet
 
 namespace epnet {
 static int gemm_launch(GemmArgs &a, cudaStream_t st)
 {
     a.n_kblocks = (a.K + kGmBK - 1) / kGmBK;
+    const int n_tiles = (a.N + a.BN - 1) / a.BN;
+    dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
+    // the opt-in shared-memory limit is a property of the function, not of a launch: always raise it to the hardware maximum so
+    // that a kernel node captured in a CUDA graph with a large request stays launchable after later, smaller launches
+    auto raise_limit = [](const void *kernel) -> int {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return (int)e;
+        return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+    };
+    if (a.BN <= 64) {  // narrow tile: X through TMEM, shared memory holds only a ring of weight k-blocks
+        int stages = a.n_kblocks < kTsMaxBStages ? a.n_kblocks : kTsMaxBStages;
+        a.stages = stages < 1 ? 1 : stages;
+        a.depth = a.n_kblocks < 3 ? a.n_kblocks : 3;  // 48 KB of X + <= 48 KB of W per CTA: two CTAs per SM
+        const size_t smem = (size_t)4 * a.depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
+        const int e = raise_limit((const void *)gemm_tf32x3_ts_kernel);
+        if (e) return e;
+        gemm_tf32x3_ts_kernel<<<grid, kGmThreads, smem, st>>>(a);
+        EPNET_RETURN_LAUNCH_STATUS();
+    }
     const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
     int stages = (int)((100 * 1024) / stage_bytes);  // <= ~100 KB per CTA: two CTAs per SM overlap each other's epilogue
     if (stages > kGmMaxStages) stages = kGmMaxStages;
@@ -412,17 +693,9 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
     if (stages < 1) stages = 1;
     a.stages = stages;
     const size_t smem = stage_bytes * stages + 1024;
-    // the opt-in limit is a property of the function, not of a launch: always raise it to the hardware maximum so that a
-    // kernel node captured in a CUDA graph with a large request stays launchable after later, smaller launches
-    auto kernel = gemm_tf32x3_kernel;
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
-    if (e != cudaSuccess) return (int)e;
-    const int n_tiles = (a.N + a.BN - 1) / a.BN;
-    dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
-    kernel<<<grid, kGmThreads, smem, st>>>(a);
+    const int e = raise_limit((const void *)gemm_tf32x3_kernel);
+    if (e) return e;
+    gemm_tf32x3_kernel<<<grid, kGmThreads, smem, st>>>(a);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 }  // namespace epnet
