@@ -68,6 +68,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Keep this the bare try_wait loop: adding a poll counter (to trap on a protocol error) measured ~50 ns slower per wait on the
+// GEMM's MMA-issue critical path, in PTX or C++ alike.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(

@@ -503,12 +503,13 @@ __global__ void __launch_bounds__(kGmThreads, 2)
 gemm_tf32x3_ts_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t gm_smem[];
-    __shared__ __align__(8) uint64_t full_a[kTsMaxAStages], empty_a[kTsMaxAStages], full_b[kTsMaxBStages], empty_b[kTsMaxBStages], accum_bar;
+    __shared__ __align__(8) uint64_t full_a[kTsMaxAStages], empty_a[kTsMaxAStages], full_b[kTsMaxBStages], empty_b[kTsMaxBStages], accum_bar,
+        acc_empty;
     __shared__ uint32_t tmem_base_slot;
     __shared__ float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * kGmBM;
+    const int m_tiles = (a.L + kGmBM - 1) / kGmBM;  // this CTA walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one n-tile
     const int ntile = blockIdx.y;
     const int BN = a.BN;                           // <= 64
     const uint32_t b_bytes = (uint32_t)BN * 128;   // one plane of the W tile
@@ -531,6 +532,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             mbar_init(&empty_b[s], 1);
         }
         mbar_init(&accum_bar, 1);
+        mbar_init(&acc_empty, kGmProducers);
         mbar_fence_init();
     }
     if (warp == 4) {
@@ -553,7 +555,6 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
         const int chunk = lane & 7;   // 16-byte chunk of the 128-byte k-row
         const int rsub = lane >> 3;   // loads: rows 32*warp + 4*i + rsub (i < 8), i.e. the warp's own TMEM lane quarter
         RowSource src;
-        src.init(a, row0 + 32 * warp + rsub, 4);
         // warp-private ring of `depth` slots of 32 rows x 128 B (chunk c of row r at c ^ (r & 7)): k-blocks are copied in with
         // cp.async `depth` ahead (no register staging, no cross-warp synchronisation), then each lane reads back its own row
         uint8_t *ring = smem + (size_t)warp * a.depth * 4096;
@@ -565,12 +566,16 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             ld_off[i] = (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4);  // chunk i of this lane's row
         }
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        int t = 0;
+        uint32_t ph = 0;
+        for (int mt = blockIdx.x, it = 0; mt < m_tiles; mt += gridDim.x, ++it) {
+        const int row0 = mt * kGmBM;
+        src.init(a, row0 + 32 * warp + rsub, 4);
         for (int j = 0; j < a.depth; ++j) {  // always `depth` groups, empty ones past the end: group index == k-block index
             if (j < a.n_kblocks) src.copy_async(a, j * kGmBK + chunk * 4, ring + j * 4096, st_off);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        int t = 0, slot = 0;
-        uint32_t ph = 0;
+        int slot = 0;
         for (int kb = 0; kb < a.n_kblocks; ++kb) {
             // k-block kb has landed when at most depth-1 newer groups are pending
             if (a.depth == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -605,10 +610,12 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
         }
 
         // ===================== epilogue =====================
-        mbar_wait(&accum_bar, 0u);
+        mbar_wait(&accum_bar, (uint32_t)it & 1u);
         tc_fence_after();
         gemm_epilogue(a, tmem_acc, corr_off, warp, lane, row0, ntile, bias_s);
         tc_fence_before();
+        mbar_arrive(&acc_empty);  // the accumulator may be overwritten by the next tile
+        }
     } else if (warp == 4) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
@@ -616,6 +623,9 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
             int t = 0, s = 0;
             uint32_t pha = 0, phb = 0;
+            for (int mt = blockIdx.x, it = 0; mt < m_tiles; mt += gridDim.x, ++it) {
+            mbar_wait(&acc_empty, ((uint32_t)it & 1u) ^ 1u);  // the epilogue of the previous tile has read the accumulator
+            tc_fence_after();
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
                 mbar_wait(&full_a[t], pha);
                 mbar_wait(&full_b[s], phb);
@@ -634,6 +644,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
                 if (++s == a.stages) { s = 0; phb ^= 1u; }
             }
             umma_commit(&accum_bar);
+            }
         }
         __syncwarp();
     } else {
@@ -642,6 +653,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
             int s = 0;
             uint32_t ph = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
                 mbar_wait(&empty_b[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
@@ -682,6 +694,10 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
         const size_t smem = (size_t)4 * a.depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
         const int e = raise_limit((const void *)gemm_tf32x3_ts_kernel);
         if (e) return e;
+        // persistent over m-tiles: two CTAs per SM in total, each walking its share of the tiles of one n-tile, so TMEM
+        // allocation, barrier set-up and CTA launch/exit are paid once per CTA instead of once per 128 rows
+        const int per_ntile = (2 * kSmCount + n_tiles - 1) / n_tiles;
+        if ((int)grid.x > per_ntile) grid.x = per_ntile;
         gemm_tf32x3_ts_kernel<<<grid, kGmThreads, smem, st>>>(a);
         EPNET_RETURN_LAUNCH_STATUS();
     }

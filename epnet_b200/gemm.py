@@ -1,4 +1,6 @@
 """Host side of the tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu): weight packing and the launch wrapper."""
+import contextlib
+
 import torch
 
 from . import pointnet2_cuda as pc
@@ -6,12 +8,36 @@ from ._lib import LIB
 
 BK = 32
 
+# "latency": a launch whose grid would leave most SMs idle is cut into narrower column tiles (shorter critical path of a single
+# forward); "throughput": keep the widest tiles (least shared-memory traffic per flop), right when several batches are in flight
+# and the GPU is full anyway.  Measured on the backbone: latency tiles 3.51 -> 3.25 ms per single batch, but -1.3 % scenes/s
+# with six batches in flight.
+_TILE_POLICY = "latency"
 
-def choose_bn(n):
-    """Output-channel tile: one tile of round_up(N,16) columns up to 256, else equal tiles <= 256."""
+
+@contextlib.contextmanager
+def tile_policy(policy):
+    global _TILE_POLICY
+    assert policy in ("latency", "throughput")
+    prev, _TILE_POLICY = _TILE_POLICY, policy
+    try:
+        yield
+    finally:
+        _TILE_POLICY = prev
+
+
+def choose_bn(n, rows=None):
+    """Output-channel tile: one tile of round_up(N,16) columns up to 256, else equal tiles <= 256.  With the row count known,
+    a grid that would leave most of the 148 SMs idle (few 128-row tiles) is cut into narrower column tiles, down to 64."""
     tiles = (n + 255) // 256
     per = (n + tiles - 1) // tiles
-    return ((per + 15) // 16) * 16
+    bn = ((per + 15) // 16) * 16
+    if rows is not None and _TILE_POLICY == "latency":
+        m_tiles = (rows + 127) // 128
+        for cand in (128, 64):
+            if cand < bn and m_tiles * ((n + bn - 1) // bn) < 100:
+                bn = cand
+    return bn
 
 
 class PackedLinear:
@@ -25,23 +51,37 @@ class PackedLinear:
         w = weight.detach().float().contiguous()
         dev = w.device
         self.N, self.K = w.shape
-        self.BN = choose_bn(self.N)
-        self.n_tiles = (self.N + self.BN - 1) // self.BN
         self.n_kblocks = (self.K + BK - 1) // BK
-        npad, kpad = self.n_tiles * self.BN, self.n_kblocks * BK
-        wp = torch.zeros(npad, kpad, device=dev)
-        wp[:self.N, :self.K] = w
-        hi = (wp.view(torch.int32) & -8192).view(torch.float32)  # 0xffffe000
-        lo = wp - hi
-        planes = torch.stack([hi, lo])                                    # (2, npad, kpad)
-        planes = planes.view(2, self.n_tiles, self.BN, self.n_kblocks, 8, 4)  # k = kb*32 + c*4 + e
-        planes = planes.permute(1, 3, 0, 2, 4, 5).contiguous()              # (tile, kb, plane, row, c, e)
-        r = torch.arange(self.BN, device=dev) % 8
-        c = torch.arange(8, device=dev)
-        src_chunk = (c[None, :] ^ r[:, None])                               # stored position p holds chunk p ^ (r%8)
-        idx = src_chunk[None, None, None, :, :, None].expand(self.n_tiles, self.n_kblocks, 2, self.BN, 8, 4)
-        self.wpack = torch.gather(planes, 4, idx).contiguous()
+        self._w = w
+        self._packs = {}
+        self.BN = choose_bn(self.N)
+        self.wpack = self._pack(self.BN)
         self.bias = None if bias is None else bias.detach().float().contiguous()
+
+    def _pack(self, bn):
+        if bn not in self._packs:
+            w, dev = self._w, self._w.device
+            n_tiles = (self.N + bn - 1) // bn
+            npad, kpad = n_tiles * bn, self.n_kblocks * BK
+            wp = torch.zeros(npad, kpad, device=dev)
+            wp[:self.N, :self.K] = w
+            hi = (wp.view(torch.int32) & -8192).view(torch.float32)  # 0xffffe000
+            lo = wp - hi
+            planes = torch.stack([hi, lo])                                    # (2, npad, kpad)
+            planes = planes.view(2, n_tiles, bn, self.n_kblocks, 8, 4)          # k = kb*32 + c*4 + e
+            planes = planes.permute(1, 3, 0, 2, 4, 5).contiguous()              # (tile, kb, plane, row, c, e)
+            r = torch.arange(bn, device=dev) % 8
+            c = torch.arange(8, device=dev)
+            src_chunk = (c[None, :] ^ r[:, None])                               # stored position p holds chunk p ^ (r%8)
+            idx = src_chunk[None, None, None, :, :, None].expand(n_tiles, self.n_kblocks, 2, bn, 8, 4)
+            self._packs[bn] = torch.gather(planes, 4, idx).contiguous()
+        return self._packs[bn]
+
+    def for_rows(self, rows):
+        """(BN, packed weights) for a launch over `rows` rows: packed on first use per tile width, then cached (warm the shapes
+        before capturing a CUDA graph)."""
+        bn = choose_bn(self.N, rows)
+        return bn, self._pack(bn)
 
     def __call__(self, x, relu=True, pool=1, out=None):
         """x (..., K) point-major rows (last dim contiguous) -> (rows / pool, N)"""
@@ -54,7 +94,8 @@ class PackedLinear:
             out = torch.empty((L // pool, self.N), dtype=torch.float32, device=x.device)
         assert out.stride(-1) == 1
         ldy = out.stride(0)
-        pc._call("gemm_tf32x3", LIB.epnet_gemm_tf32x3, x2, L, self.K, self.N, x2.data_ptr(), ldx, self.wpack.data_ptr(), self.BN,
+        bn, wpack = self.for_rows(L)
+        pc._call("gemm_tf32x3", LIB.epnet_gemm_tf32x3, x2, L, self.K, self.N, x2.data_ptr(), ldx, wpack.data_ptr(), bn,
                  None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), pool, out.data_ptr(), ldy)
         return out
 
@@ -80,8 +121,9 @@ class PackedDeconv:
         assert out.shape == (B, h * self.k, w * self.k, self.cout) and out.stride(-1) == 1
         assert out.stride(-3) == w * self.k * ldo and out.stride(0) == h * self.k * w * self.k * ldo
         lin = self.lin
+        bn, wpack = lin.for_rows(B * h * w)
         pc._call("deconv_nhwc_tf32x3", LIB.epnet_deconv_nhwc_tf32x3, x, B, h, w, self.cin, self.k, self.cout, x.data_ptr(), ldx,
-                 lin.wpack.data_ptr(), lin.BN, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(), ldo)
+                 wpack.data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(), ldo)
         return out
 
 
@@ -109,7 +151,8 @@ class PackedConv3x3:
             out = torch.empty((B, Ho, Wo, self.cout), dtype=torch.float32, device=x.device)
         assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
         lin = self.lin
+        bn, wpack = lin.for_rows(B * Ho * Wo)
         pc._call("conv3x3_nhwc_tf32x3", LIB.epnet_conv3x3_nhwc_tf32x3, x, B, H, W, self.cin_p, self.cout, self.stride, x.data_ptr(),
-                 lin.wpack.data_ptr(), lin.BN, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(),
+                 wpack.data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(),
                  out.stride(-2))
         return out

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
-from .gemm import PackedConv3x3, PackedDeconv, PackedLinear
+from .gemm import PackedConv3x3, PackedDeconv, PackedLinear, tile_policy
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -105,10 +105,12 @@ class _FusionPM:
         return self.fuse(cat, relu=True, out=out)
 
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm"):
-        """layout "pm": point-major activations + tcgen05 3xTF32 GEMMs (default); "cm": channel-major + cuBLAS."""
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency"):
+        """layout "pm": point-major activations + tcgen05 3xTF32 GEMMs (default); "cm": channel-major + cuBLAS.
+        tiles: gemm.tile_policy for every GEMM launch of this runner ("latency" for one batch at a time)."""
         assert layout in ("pm", "cm")
         self.layout = layout
+        self.tiles = tiles
         if model.training:
             raise RuntimeError("BackboneRunner folds BatchNorm: call model.eval() first (train mode: use model(...) itself)")
         c = model.config
@@ -174,6 +176,10 @@ class BackboneRunner:
         return x
 
     def _forward(self):
+        with tile_policy(self.tiles):
+            return self._forward_impl()
+
+    def _forward_impl(self):
         c, B, N, dev = self.cfg, self.B, self.N, self.device
         main = torch.cuda.current_stream(dev)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -508,6 +514,7 @@ class PipelinedRunner:
 
     def __init__(self, model, batch, npoints, device, depth=2, **kw):
         self.device = device
+        kw.setdefault("tiles", "throughput")  # several batches in flight fill the GPU: widest tiles, least traffic per flop
         self.runners = [BackboneRunner(model, batch, npoints, device, **kw) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
         self.kernel_launches_per_replay = self.runners[0].kernel_launches_per_replay

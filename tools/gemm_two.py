@@ -1,4 +1,4 @@
-"""Two launches of the tcgen05 GEMM for an ncu capture: the 64->64 stride-2 image convolution (384x1280) and the 1x1 fusion conv
+"""Two launches of the tcgen05 GEMM for an ncu capture: the first image convolution (3->64, 384x1280) and the 1x1 fusion conv
 shape (983040 x 64 -> 32).  cudaProfilerStart/Stop bracket exactly one launch of each."""
 import os
 import sys
@@ -8,8 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from epnet_b200.gemm import PackedConv3x3, PackedLinear  # noqa: E402
 
-conv = PackedConv3x3(torch.randn(64, 64, 3, 3, device="cuda") / 24, torch.randn(64, device="cuda"), stride=2)
-x = torch.randn(2, 384, 1280, 64, device="cuda")
+conv = PackedConv3x3(torch.randn(64, 3, 3, 3, device="cuda") / 5, torch.randn(64, device="cuda"), stride=1)
+x = torch.randn(2, 384, 1280, 4, device="cuda")
 lin = PackedLinear(torch.randn(32, 64, device="cuda") / 8, torch.randn(32, device="cuda"))
 X = torch.randn(983040, 64, device="cuda")
 out = torch.empty(983040, 32, device="cuda")
