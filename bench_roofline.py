@@ -189,8 +189,9 @@ def measure(model, runner, dev_pool, device, world):
     # per kernel NAME: total time, algorithmic bytes / flops over all its launches of one step
     by_name = {}
     for (name, ints), (tot, cnt) in agg.items():
-        # the implicit-GEMM convolution is the same device kernel as the GEMM (conv mode of gemm_tf32x3_kernel)
-        e = by_name.setdefault("gemm_tf32x3_kernel" if name in ("gemm_tf32x3", "conv3x3_nhwc_tf32x3") else name,
+        # plain, implicit-convolution and transposed-convolution launches are the same device code: gemm_tf32x3_kernel
+        # (tiles wider than 64 columns) or gemm_tf32x3_ts_kernel (A operand through TMEM, tiles of <= 64 columns)
+        e = by_name.setdefault("gemm_tf32x3_kernel" if name in ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3") else name,
                                {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
         e["time"] += tot / reps
         e["launches"] += cnt // reps
@@ -202,6 +203,10 @@ def measure(model, runner, dev_pool, device, world):
             ho, wo = (h_ - 1) // st_ + 1, (w_ - 1) // st_ + 1
             e["flops"] += 2.0 * b_ * ho * wo * 9 * ci_ * co_ * (cnt // reps)
             e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * 9 * ci_ * co_ + b_ * ho * wo * co_) * (cnt // reps)
+        if name == "deconv_nhwc_tf32x3":  # (b, h, w, cin, k, co, ldx, BN, relu, ldo): every input pixel -> a k x k x co patch
+            b_, h_, w_, ci_, k_, co_ = ints[:6]
+            e["flops"] += 2.0 * b_ * h_ * w_ * ci_ * k_ * k_ * co_ * (cnt // reps)
+            e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * ci_ * k_ * k_ * co_ + b_ * h_ * w_ * k_ * k_ * co_) * (cnt // reps)
     bf16_peak = 1383.2
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:

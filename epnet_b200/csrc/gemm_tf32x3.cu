@@ -568,13 +568,17 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         int t = 0;
         uint32_t ph = 0;
+        // the first `depth` k-blocks of a tile are requested before the previous tile's epilogue, so their latency hides behind it
+        auto prefetch_tile = [&](int mt) {
+            src.init(a, mt * kGmBM + 32 * warp + rsub, 4);
+            for (int j = 0; j < a.depth; ++j) {  // always `depth` groups, empty ones past the end: group index == k-block index
+                if (j < a.n_kblocks) src.copy_async(a, j * kGmBK + chunk * 4, ring + j * 4096, st_off);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        };
+        if ((int)blockIdx.x < m_tiles) prefetch_tile(blockIdx.x);
         for (int mt = blockIdx.x, it = 0; mt < m_tiles; mt += gridDim.x, ++it) {
         const int row0 = mt * kGmBM;
-        src.init(a, row0 + 32 * warp + rsub, 4);
-        for (int j = 0; j < a.depth; ++j) {  // always `depth` groups, empty ones past the end: group index == k-block index
-            if (j < a.n_kblocks) src.copy_async(a, j * kGmBK + chunk * 4, ring + j * 4096, st_off);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
         int slot = 0;
         for (int kb = 0; kb < a.n_kblocks; ++kb) {
             // k-block kb has landed when at most depth-1 newer groups are pending
@@ -608,6 +612,8 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             if (++t == a_stages) { t = 0; ph ^= 1u; }
             if (++slot == a.depth) slot = 0;
         }
+
+        if (mt + (int)gridDim.x < m_tiles) prefetch_tile(mt + gridDim.x);  // every ring slot of this tile has been read
 
         // ===================== epilogue =====================
         mbar_wait(&accum_bar, (uint32_t)it & 1u);

@@ -27,9 +27,11 @@ def tile_policy(policy):
 
 
 def choose_bn(n, rows=None):
-    """Output-channel tile: one tile of round_up(N,16) columns up to 256, else equal tiles <= 256.  With the row count known,
+    """Output-channel tile: equal tiles of <= 64 columns for N <= 128, else of <= 256 columns (rounded up to 16).  With the row count known,
     a grid that would leave most of the 148 SMs idle (few 128-row tiles) is cut into narrower column tiles, down to 64."""
-    tiles = (n + 255) // 256
+    # up to 128 columns: tiles of <= 64, which run on the A-from-TMEM kernel (two of them re-read X, but measured faster than one
+    # 128-column tile of the shared-memory-operand kernel: 835 -> 849 scenes/s on the backbone)
+    tiles = (n + 63) // 64 if n <= 128 else (n + 255) // 256
     per = (n + tiles - 1) // tiles
     bn = ((per + 15) // 16) * 16
     if rows is not None and _TILE_POLICY == "latency":

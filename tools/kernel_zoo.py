@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from epnet_b200 import pointnet2_cuda as pc  # noqa: E402
 from epnet_b200 import scenes  # noqa: E402
-from epnet_b200.gemm import PackedConv3x3, PackedLinear  # noqa: E402
+from epnet_b200.gemm import PackedConv3x3, PackedDeconv, PackedLinear  # noqa: E402
 from epnet_b200 import roipool3d_utils  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -64,6 +64,16 @@ for _ in range(reps):
     ximg = torch.randn(2, 96, 320, 128, device=dev)
     conv = PackedConv3x3(torch.randn(256, 128, 3, 3, device=dev) / 34, torch.zeros(256, device=dev), stride=1)
     yimg = conv(ximg, relu=True)
+    # --- the A-from-TMEM kernel (tiles of <= 64 columns): 64->64 stride-2 convolution at 384x1280, the 1x1 fusion conv shape, and a
+    #     transposed convolution (128 -> 16, k = 4) writing into the 64-channel concat
+    xbig = torch.randn(2, 384, 1280, 64, device=dev)
+    conv_ts = PackedConv3x3(torch.randn(64, 64, 3, 3, device=dev) / 24, torch.zeros(64, device=dev), stride=2)
+    conv_ts(xbig, relu=True)
+    lin_ts = PackedLinear(torch.randn(32, 64, device=dev) / 8, torch.zeros(32, device=dev))
+    lin_ts(xbig.view(-1, 64), relu=True)
+    cat2 = torch.empty(2, 384, 1280, 64, device=dev)
+    PackedDeconv(torch.randn(128, 16, 4, 4, device=dev) / 11, None)(ximg, cat2[..., 16:32])
+    del xbig
     xyp = (torch.rand(2, 16384, 2, generator=g) * 2 - 1).to(dev)
     gout = torch.empty(2 * 16384, 256, device=dev)
     pc.grid_gather_nhwc_pm_wrapper(2, 256, 96, 320, 16384, yimg, xyp, False, gout)
