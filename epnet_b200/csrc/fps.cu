@@ -515,6 +515,78 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
     for (int e = tid; e < m * aux_dim && aux_out; e += 1024) aux_out[e] = __ldg(aux_in + (size_t)idx[e / aux_dim] * aux_dim + e % aux_dim);
 }
 
+// ---- small clouds (N <= 512: RCNN-stage RoIs, the last backbone level): one warp per scene, several scenes per CTA ----
+// Lane l keeps points l, l+32, ... (coordinates, running distance) in registers; coordinates also sit in shared memory so the
+// winner's can be broadcast-read.  No sort, no buckets, no barrier: an iteration is PPL distance updates per lane and one warp
+// arg-max (max distance bits, then min compact key = the reference's tie order).
+template <int PPL>
+__global__ void __launch_bounds__(128)
+fps_warp_kernel(int scenes, int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
+                float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
+{
+    __shared__ float s_xyz[4][PPL * 32 * 3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int scene = blockIdx.x * 4 + warp;
+    if (scene >= scenes) return;
+    xyz += (size_t)scene * n * 3;
+    temp += (size_t)scene * n;
+    idx += (size_t)scene * m;
+    float *sx = s_xyz[warp];
+    for (int e = lane; e < n * 3; e += 32) sx[e] = __ldg(xyz + e);
+    __syncwarp();
+
+    float px[PPL], py[PPL], pz[PPL], t[PPL];
+    uint32_t ck[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+        const int k = lane + 32 * i;
+        const bool ok = k < n;
+        px[i] = ok ? sx[3 * k] : 0.f;
+        py[i] = ok ? sx[3 * k + 1] : 0.f;
+        pz[i] = ok ? sx[3 * k + 2] : 0.f;
+        t[i] = ok ? temp[k] : -1.f;  // a slot without a point never wins: every real running distance is >= 0
+        ck[i] = ok ? fps_compact_key((uint32_t)k, L, qbits) : 0xffffffffu;
+    }
+    if (lane == 0) idx[0] = 0;
+    uint32_t last = 0;
+    for (int j = 1; j < m; ++j) {
+        const float lx = sx[3 * last], ly = sx[3 * last + 1], lz = sx[3 * last + 2];
+        // candidate = (distance bits, inverted compact key) as one 64-bit integer: larger distance wins, then smaller key; the
+        // lane's PPL candidates meet in a tournament tree (depth log2 PPL) instead of a serial compare chain
+        unsigned long long cand[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            t[i] = fminf(t[i], sqdist_ref(px[i], py[i], pz[i], lx, ly, lz));  // padding slots: fminf(-1, d) stays -1
+            cand[i] = t[i] < 0.f ? 0ull : ((unsigned long long)__float_as_uint(t[i]) << 32) | (unsigned long long)(~ck[i]);
+        }
+#pragma unroll
+        for (int w = 1; w < PPL; w <<= 1)
+#pragma unroll
+            for (int i = 0; i + w < PPL; i += 2 * w) cand[i] = cand[i] > cand[i + w] ? cand[i] : cand[i + w];
+        uint32_t bits = (uint32_t)(cand[0] >> 32), tie = ~(uint32_t)cand[0];
+        warp_argmax(bits, tie);
+        last = fps_key_to_index(tie, L, qbits);
+        if (lane == 0) idx[j] = (int)last;
+    }
+#pragma unroll
+    for (int i = 0; i < PPL; ++i)  // temp is an in/out buffer in the reference: leave the final running distances behind
+        if (lane + 32 * i < n) temp[lane + 32 * i] = t[i];
+    if (new_xyz || aux_out) {
+        __syncwarp();  // idx[] written by lane 0 is visible to the warp
+        for (int e = lane; e < m * 3 && new_xyz; e += 32) new_xyz[(size_t)scene * m * 3 + e] = sx[3 * idx[e / 3] + e % 3];
+        for (int e = lane; e < m * aux_dim && aux_out; e += 32)
+            aux_out[(size_t)scene * m * aux_dim + e] = __ldg(aux_in + ((size_t)scene * n + idx[e / aux_dim]) * aux_dim + e % aux_dim);
+    }
+}
+
+template <int PPL>
+static int launch_warp(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
+                       const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
+{
+    fps_warp_kernel<PPL><<<(b + 3) / 4, 128, 0, st>>>(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
 template <int NW, int kBuckets, int kSlots>
 static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
@@ -572,7 +644,9 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
 #define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st
-        if (n <= 256) return launch_bucket<1, 8, 1>(EPNET_FPS_ARGS);    //   8 buckets of  32, one warp, no barrier
+        if (n <= 128) return launch_warp<4>(EPNET_FPS_ARGS);            // one warp per scene, points in registers, no buckets
+        if (n <= 256) return launch_warp<8>(EPNET_FPS_ARGS);
+        if (n <= 512) return launch_warp<16>(EPNET_FPS_ARGS);
         if (n <= 1024) return launch_bucket<4, 8, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
         if (n <= 4096) return launch_bucket<16, 8, 1>(EPNET_FPS_ARGS);  // 128 buckets of  32
         return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
