@@ -83,6 +83,10 @@ class PackedLinear:
         """(BN, packed weights) for a launch over `rows` rows: packed on first use per tile width, then cached (warm the shapes
         before capturing a CUDA graph)."""
         bn = choose_bn(self.N, rows)
+        if self.K <= 128 and bn > 64:
+            # at most 4 k-blocks per tile: the per-tile cost is set-up and epilogue, which the persistent narrow-tile kernel
+            # amortises (measured: transposed conv 128 -> 16 x 4 x 4, 83 -> 58 us), even though X is then read once per 64 columns
+            bn = choose_bn(min(self.N, 128))
         return bn, self._pack(bn)
 
     def __call__(self, x, relu=True, pool=1, out=None):
