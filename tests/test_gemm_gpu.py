@@ -20,6 +20,9 @@ def _ref(x, w, b, relu, pool):
 @pytest.mark.parametrize("L,K,N,relu,pool", [
     (128, 32, 16, False, 1), (256, 32, 16, True, 1), (1000, 99, 64, True, 1), (4096, 259, 196, True, 1), (512, 1536, 512, True, 1),
     (4096, 6, 32, True, 16), (2048, 99, 128, True, 32), (384, 515, 384, False, 1), (96, 64, 96, True, 2), (33, 35, 17, False, 1),
+    # narrow-tile persistent kernel: more 128-row tiles than resident CTAs (every CTA walks several tiles, barrier phases wrap),
+    # ragged last tile, two column tiles, pooled epilogue; and a wide-tile launch under both tile policies
+    (89600 + 77, 70, 48, True, 1), (65536, 33, 128, True, 16), (40000, 200, 100, False, 1), (3000, 300, 512, True, 1),
 ])
 def test_gemm_matches_fp64(L, K, N, relu, pool):
     from epnet_b200.gemm import PackedLinear
@@ -44,6 +47,22 @@ def test_gemm_matches_fp64(L, K, N, relu, pool):
     torch.backends.cuda.matmul.allow_tf32 = False
     if K >= 64 and pool == 1 and not relu:
         assert (tf32.double() - want).abs().max().item() > 20 * err
+
+
+def test_tile_policies_agree():
+    """latency tiles (narrow, more CTAs) and throughput tiles (widest) are two schedules of the same arithmetic per output"""
+    from epnet_b200.gemm import PackedLinear, tile_policy
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(600, 777, generator=g).cuda()
+    lin = PackedLinear((torch.randn(512, 777, generator=g) / 28).cuda(), torch.randn(512, generator=g).cuda())
+    with tile_policy("latency"):
+        bn_l, a = lin.for_rows(600)[0], lin(x)
+    with tile_policy("throughput"):
+        bn_t, b = lin.for_rows(600)[0], lin(x)
+    assert bn_l < bn_t
+    want = _ref(x, lin._w, lin.bias, True, 1)
+    for y in (a, b):
+        assert (y.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
 
 
 def test_gemm_strided_input_and_output():
