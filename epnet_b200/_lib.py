@@ -15,6 +15,8 @@ SIGNATURES = {
     "epnet_gather_points": [_c_int] * 4 + [_c_void_p] * 4,
     "epnet_gather_points_grad": [_c_int] * 4 + [_c_void_p] * 4,
     "epnet_ball_query": [_c_int] * 3 + [_c_float, _c_int] + [_c_void_p] * 4,
+    "epnet_bucket_cloud": [_c_int] * 3 + [_c_void_p] * 4,
+    "epnet_ball_query_sorted": [_c_int] * 3 + [_c_float, _c_int] + [_c_void_p] * 5,
     "epnet_group_points": [_c_int] * 5 + [_c_void_p] * 4,
     "epnet_group_points_grad": [_c_int] * 5 + [_c_void_p] * 4,
     "epnet_three_nn": [_c_int] * 3 + [_c_void_p] * 5,

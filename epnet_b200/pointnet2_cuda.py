@@ -77,9 +77,50 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, gr
     return 1
 
 
+SORTED_QUERY_MIN_N, SORTED_QUERY_MAX_N, SORTED_QUERY_MAX_NSAMPLE = 8192, 16384, 64
+# (weakref to the cloud tensor, its version counter, stream-capture flag, buckets): QueryAndGroup queries one cloud once per radius
+_bucket_cache = None
+
+
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
+    """Reference signature (ball_query.cpp:14-25).  Large clouds go through the sorted-bucket search (same result; the scratch
+    it needs is allocated here, and the sort is reused while the SAME tensor object is queried again unmodified -- the MSG
+    modules query every cloud once per radius); everything else through the exhaustive scan."""
+    global _bucket_cache
+    if SORTED_QUERY_MIN_N <= n <= SORTED_QUERY_MAX_N and 1 <= nsample <= SORTED_QUERY_MAX_NSAMPLE and m > 0 and b > 0:
+        import torch
+        # a sort recorded outside a CUDA-graph capture must not be baked into the graph (replays see new data), nor the reverse
+        capturing = torch.cuda.is_current_stream_capturing()
+        hit = (_bucket_cache is not None and _bucket_cache[0]() is xyz_tensor and _bucket_cache[1] == xyz_tensor._version
+               and _bucket_cache[2] == capturing)
+        if not hit:
+            import weakref
+            _bucket_cache = (weakref.ref(xyz_tensor), xyz_tensor._version, capturing, bucket_cloud(xyz_tensor))
+        ball_query_sorted_wrapper(b, m, radius, nsample, new_xyz_tensor, _bucket_cache[3], idx_tensor)
+        return 1
     _call("ball_query", LIB.epnet_ball_query, xyz_tensor, b, n, m, float(radius), nsample, _f(new_xyz_tensor, "new_xyz"),
           _f(xyz_tensor, "xyz"), _i(idx_tensor, "idx"))
+    return 1
+
+
+def bucket_cloud(xyz_tensor):
+    """(sorted (B, npad, 4), boxes (B, npad/64, 8)) of a cloud (B, n, 3), n <= 16384: see epnet_bucket_cloud.  One sort serves
+    every ball query (any radius, nsample <= 64) against that cloud."""
+    import torch
+    b, n = xyz_tensor.shape[0], xyz_tensor.shape[1]
+    npad = 64
+    while npad < n:
+        npad *= 2
+    srt = torch.empty((b, npad, 4), dtype=torch.float32, device=xyz_tensor.device)
+    boxes = torch.empty((b, npad // 64, 8), dtype=torch.float32, device=xyz_tensor.device)
+    _call("bucket_cloud", LIB.epnet_bucket_cloud, xyz_tensor, b, n, npad, _f(xyz_tensor, "xyz"), srt.data_ptr(), boxes.data_ptr())
+    return srt, boxes
+
+
+def ball_query_sorted_wrapper(b, m, radius, nsample, new_xyz_tensor, buckets, idx_tensor):
+    srt, boxes = buckets
+    _call("ball_query_sorted", LIB.epnet_ball_query_sorted, new_xyz_tensor, b, srt.shape[1], m, float(radius), nsample,
+          _f(new_xyz_tensor, "new_xyz"), srt.data_ptr(), boxes.data_ptr(), _i(idx_tensor, "idx"))
     return 1
 
 

@@ -190,6 +190,7 @@ class BackboneRunner:
         # ---- FPS chain of all levels (coordinates only) on its own stream ----
         ready = torch.cuda.Event()
         ready.record(main)
+        self._ready = ready
         l_xyz, l_xy, fps_done = [xyz0], [xyn], []
         with torch.cuda.stream(self.s_fps):
             self.s_fps.wait_event(ready)
@@ -359,6 +360,16 @@ class BackboneRunner:
         # Geometry-only work depends on the sampled coordinates alone, not on features: every level's ball queries and
         # three_nn searches are issued on side streams as soon as the FPS level they need is done, off the feature path.
         bq, nn = {}, {}
+        # large clouds are Morton-sorted into 64-point buckets once per level (as soon as the level's coordinates exist, i.e. in
+        # parallel with the FPS that samples them); both radii of the level then search the buckets instead of the whole cloud
+        buckets = {}
+        with torch.cuda.stream(self.s_geo[0]):
+            for k in range(len(self.sa_pm)):
+                if pc.SORTED_QUERY_MIN_N <= l_xyz[k].shape[1] <= pc.SORTED_QUERY_MAX_N:
+                    self.s_geo[0].wait_event(self._ready if k == 0 else fps_done[k - 1])
+                    ev = torch.cuda.Event()
+                    buckets[k] = (pc.bucket_cloud(l_xyz[k]), ev)
+                    ev.record(self.s_geo[0])
         for si in range(2):
             with torch.cuda.stream(self.s_geo[si]):
                 for k, (npoint, scales) in enumerate(self.sa_pm):
@@ -367,7 +378,11 @@ class BackboneRunner:
                     radius, ns, _ = scales[si]
                     self.s_geo[si].wait_event(fps_done[k])
                     bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
-                    pc.ball_query_wrapper(B, l_xyz[k].shape[1], npoint, radius, ns, l_xyz[k + 1], l_xyz[k], bidx)
+                    if k in buckets and ns <= pc.SORTED_QUERY_MAX_NSAMPLE:
+                        self.s_geo[si].wait_event(buckets[k][1])
+                        pc.ball_query_sorted_wrapper(B, npoint, radius, ns, l_xyz[k + 1], buckets[k][0], bidx)
+                    else:
+                        pc.ball_query_wrapper(B, l_xyz[k].shape[1], npoint, radius, ns, l_xyz[k + 1], l_xyz[k], bidx)
                     ev = torch.cuda.Event()
                     ev.record(self.s_geo[si])
                     bq[(k, si)] = (bidx, ev)

@@ -48,6 +48,16 @@ int epnet_gather_points_grad(int b, int c, int n, int npoints, const float *grad
  * idx (B,M,nsample) arrives zeroed. */
 int epnet_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx, void *stream);
 
+/* The same result (bit-identical idx) through a spatially sorted copy of the cloud, for callers that can provide scratch:
+ * epnet_bucket_cloud sorts each scene by Morton key and writes `sorted` (B, npad, 4) = (x, y, z, original index as int bits;
+ * padding entries hold index -1) and `boxes` (B, npad/64, 8) = exact min/max corner of every 64 sorted points; npad is a
+ * power of two with n <= npad <= 16384.  epnet_ball_query_sorted then answers any number of radius / nsample <= 64 queries
+ * against it (ball_query_gpu.cu:23-44 semantics: first nsample indices in ascending order, first-hit padding, zeros kept when
+ * the ball is empty), scanning only the buckets whose box meets the ball. */
+int epnet_bucket_cloud(int b, int n, int npad, const float *xyz, float *sorted, float *boxes, void *stream);
+int epnet_ball_query_sorted(int b, int npad, int m, float radius, int nsample, const float *new_xyz, const float *sorted,
+                            const float *boxes, int *idx, void *stream);
+
 /* replaces group_points_kernel_launcher_fast (group_points_gpu.h:13): out[b,c,p,s] = points[b,c,idx[b,p,s]] */
 int epnet_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out, void *stream);
 /* replaces group_points_grad_kernel_launcher_fast (group_points_gpu.h:19); grad_points arrives zeroed */

@@ -175,3 +175,29 @@ def test_cpu_tensors_are_refused():
     x = torch.zeros(1, 8, 3)
     with pytest.raises(ValueError):
         pointnet2_cuda.furthest_point_sampling_wrapper(1, 8, 2, x, torch.zeros(1, 8), torch.zeros(1, 2, dtype=torch.int32))
+
+
+# ------------------------------------------------------------------ ball query through sorted buckets
+@pytest.mark.parametrize("kind,n,m,radius,nsample", [
+    ("uniform", 2048, 512, 0.15, 16), ("gauss", 4096, 1024, 0.5, 32), ("lattice", 5000, 700, 0.3, 64), ("identical", 300, 50, 0.1, 16),
+    ("uniform", 16384, 4096, 0.02, 16), ("gauss", 16384, 1000, 100.0, 32), ("gauss", 3001, 333, 0.4, 1), ("uniform", 64, 64, 0.5, 7),
+])
+def test_ball_query_sorted_bit_exact(kind, n, m, radius, nsample):
+    """The sorted-bucket search must return exactly what the exhaustive scan returns: duplicates, empty balls (tiny radius),
+    balls that hold the whole cloud (huge radius), nsample 1..64, n not a power of two."""
+    from epnet_b200 import pointnet2_cuda as pc
+    xyz = cloud(21, 2, n, kind, dup_frac=0.05 if n > 100 else 0.0)
+    new_xyz = np.ascontiguousarray(xyz[:, :m] + (0.01 if kind == "lattice" else 0.0)).astype(np.float32)
+    want = oracle.ball_query(radius, nsample, xyz, new_xyz)
+    x, q = dev(xyz), dev(new_xyz)
+    idx = torch.zeros((2, m, nsample), dtype=torch.int32, device="cuda")
+    buckets = pc.bucket_cloud(x)
+    srt = buckets[0].cpu().numpy()
+    orig = srt[..., 3].view(np.int32)
+    for s in range(2):  # the sorted copy is a permutation of the cloud plus padding
+        valid = orig[s] >= 0
+        assert sorted(orig[s][valid].tolist()) == list(range(n))
+        np.testing.assert_array_equal(srt[s][valid][:, :3], xyz[s][orig[s][valid]])
+    pc.ball_query_sorted_wrapper(2, m, radius, nsample, q, buckets, idx)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(idx.cpu().numpy(), want)
