@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 in cuDNN/cuBLAS (default 0: strict fp32 in both arms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="ours: run eagerly instead of replaying the captured CUDA graph")
-    ap.add_argument("--pipeline", type=int, default=6, help="ours: batches kept in flight (PipelinedRunner depth; 1 = one at a time)")
+    ap.add_argument("--pipeline", type=int, default=8, help="ours: batches kept in flight (PipelinedRunner depth; 1 = one at a time)")
     ap.add_argument("--layout", choices=["pm", "cm"], default="pm")
     ap.add_argument("--mode", choices=["infer", "train"], default="infer",
                     help="train = BASELINE.json configs[2]: forward+backward+Adam through the module path, train-mode BN, DDP gradient "
