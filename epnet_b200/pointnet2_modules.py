@@ -1,10 +1,11 @@
-"""Set-abstraction and feature-propagation modules with the interface, attribute names and return
-values of the reference's pointnet2_lib/pointnet2/pointnet2_modules.py, on the B200 ops.
+"""Set-abstraction (SA) and feature-propagation (FP) modules behind the interface of the reference's
+pointnet2_lib/pointnet2/pointnet2_modules.py: same constructor keywords, the attribute names checkpoints are keyed by
+(`groupers`, `mlps`, `mlp`), same return values -- including the FPS indices EPNet's fork returns as a third value
+(pointnet2_modules.py:72), which LI-Fusion uses to carry pixel coordinates along (lib/net/pointnet2_msg.py:217-219).
 
-`ops` selects the op set (epnet_b200.pointnet2_utils.make_ops); None = the product kernels.
+`ops` selects the op set (epnet_b200.pointnet2_utils.make_ops); None = the product kernels.  These modules are the
+op-by-op ("module") path: training and the drop-in use; inference goes through runner.py, which fuses most of this.
 """
-from typing import List
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -12,97 +13,86 @@ import torch.nn.functional as F
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
+_POOLS = {"max_pool": F.max_pool2d, "avg_pool": F.avg_pool2d}
+
 
 class _PointnetSAModuleBase(nn.Module):
+    """Sample centres (FPS unless the caller brings them), then per scale: group, shared MLP, pool over the group."""
+
     def __init__(self):
         super().__init__()
-        self.npoint = None
-        self.groupers = None
-        self.mlps = None
+        self.npoint, self.groupers, self.mlps = None, None, None
         self.pool_method = "max_pool"
         self._ops = pointnet2_utils.OPS
 
-    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None):
-        """pointnet2_modules.py:19-72.
-        xyz (B,N,3), features (B,C,N) -> (new_xyz (B,npoint,3), new_features (B,sum_k mlps[k][-1],npoint),
-        idx (B,npoint) int32 FPS indices or None).  EPNet's fork returns the FPS indices as a third value
-        (:72); LI-Fusion uses them to carry pixel coordinates along (lib/net/pointnet2_msg.py:217-219)."""
-        ops = self._ops
-        new_features_list = []
-        idx = None
-        if new_xyz is None and self.npoint is not None:
-            xyz_flipped = xyz.transpose(1, 2).contiguous()
-            idx = ops.furthest_point_sample(xyz, self.npoint)
-            new_xyz = ops.gather_operation(xyz_flipped, idx).transpose(1, 2).contiguous()
+    def _centres(self, xyz):
+        """(centres (B,npoint,3), FPS indices (B,npoint)); (None, None) for a GroupAll level (pointnet2_modules.py:36-45)"""
+        if self.npoint is None:
+            return None, None
+        picked = self._ops.furthest_point_sample(xyz, self.npoint)
+        as_rows = self._ops.gather_operation(xyz.transpose(1, 2).contiguous(), picked)
+        return as_rows.transpose(1, 2).contiguous(), picked
 
+    def forward(self, xyz, features=None, new_xyz=None):
+        """xyz (B,N,3), features (B,C,N) -> (new_xyz (B,npoint,3), (B, sum of the scales' last widths, npoint), FPS idx | None)"""
+        if self.pool_method not in _POOLS:
+            raise NotImplementedError
+        fps_idx = None
+        if new_xyz is None:
+            new_xyz, fps_idx = self._centres(xyz)
+        per_scale = []
         for grouper, mlp in zip(self.groupers, self.mlps):
-            new_features = grouper(xyz, new_xyz, features)  # (B, C, npoint, nsample)
-            new_features = mlp(new_features)  # (B, mlp[-1], npoint, nsample)
-            if self.pool_method == "max_pool":
-                new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
-            elif self.pool_method == "avg_pool":
-                new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
-            else:
-                raise NotImplementedError
-            new_features_list.append(new_features.squeeze(-1))  # (B, mlp[-1], npoint)
-
-        return new_xyz, torch.cat(new_features_list, dim=1), idx
+            y = mlp(grouper(xyz, new_xyz, features))                      # (B, width, npoint, nsample)
+            y = _POOLS[self.pool_method](y, kernel_size=[1, y.size(3)])   # pool the nsample axis (pointnet2_modules.py:59-66)
+            per_scale.append(y.squeeze(-1))
+        return new_xyz, torch.cat(per_scale, dim=1), fps_idx
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):
-    """Set abstraction with multi-scale grouping (pointnet2_modules.py:75-109)."""
+    """SA level with multi-scale grouping: one (radius, nsample, MLP) triple per scale (pointnet2_modules.py:75-109)."""
 
-    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int], mlps: List[List[int]], bn: bool = True,
-                 use_xyz: bool = True, pool_method="max_pool", instance_norm=False, ops=None):
+    def __init__(self, *, npoint, radii, nsamples, mlps, bn=True, use_xyz=True, pool_method="max_pool", instance_norm=False, ops=None):
         super().__init__()
-        assert len(radii) == len(nsamples) == len(mlps)
-        if ops is not None:
-            self._ops = ops
-        self.npoint = npoint
-        self.groupers = nn.ModuleList()
-        self.mlps = nn.ModuleList()
-        for radius, nsample, mlp_spec in zip(radii, nsamples, mlps):
-            self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz, ops=self._ops)
-                                 if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+        if not (len(radii) == len(nsamples) == len(mlps)):
+            raise AssertionError("radii, nsamples and mlps describe the same scales")
+        self._ops = ops or self._ops
+        self.npoint, self.pool_method = npoint, pool_method
+        self.groupers, self.mlps = nn.ModuleList(), nn.ModuleList()
+        for radius, nsample, widths in zip(radii, nsamples, mlps):
+            if npoint is None:
+                self.groupers.append(pointnet2_utils.GroupAll(use_xyz))
+            else:
+                self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz, ops=self._ops))
             if use_xyz:
-                mlp_spec[0] += 3  # in place, like the reference (:105-106): callers see the widened spec
-            self.mlps.append(pt_utils.SharedMLP(mlp_spec, bn=bn, instance_norm=instance_norm))
-        self.pool_method = pool_method
+                widths[0] += 3  # the caller's list is widened in place, as the reference does (:105-106) and its callers expect
+            self.mlps.append(pt_utils.SharedMLP(widths, bn=bn, instance_norm=instance_norm))
 
 
 class PointnetSAModule(PointnetSAModuleMSG):
-    """Single-scale set abstraction (pointnet2_modules.py:112-130)."""
+    """The single-scale special case (pointnet2_modules.py:112-130)."""
 
-    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None, bn: bool = True,
-                 use_xyz: bool = True, pool_method="max_pool", instance_norm=False, ops=None):
-        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn, use_xyz=use_xyz,
+    def __init__(self, *, mlp, npoint=None, radius=None, nsample=None, bn=True, use_xyz=True, pool_method="max_pool",
+                 instance_norm=False, ops=None):
+        super().__init__(npoint=npoint, radii=[radius], nsamples=[nsample], mlps=[mlp], bn=bn, use_xyz=use_xyz,
                          pool_method=pool_method, instance_norm=instance_norm, ops=ops)
 
 
 class PointnetFPModule(nn.Module):
-    """Feature propagation (pointnet2_modules.py:133-173): inverse-distance interpolation of the coarser
-    level's features onto the finer level's points, concatenation with the skip features, shared MLP."""
+    """FP level (pointnet2_modules.py:133-173): every fine point takes the inverse-distance blend of its three nearest coarse
+    points' features, the skip features are stacked underneath, a shared MLP follows."""
 
-    def __init__(self, *, mlp: List[int], bn: bool = True, activation=nn.ReLU(inplace=True), ops=None):
+    def __init__(self, *, mlp, bn=True, activation=nn.ReLU(inplace=True), ops=None):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn, activation=activation)
         self._ops = ops or pointnet2_utils.OPS
 
-    def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
-                known_feats: torch.Tensor) -> torch.Tensor:
-        """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m) -> (B,mlp[-1],n)."""
-        ops = self._ops
-        if known is not None:
-            dist, idx = ops.three_nn(unknown, known)
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = torch.sum(dist_recip, dim=2, keepdim=True)
-            weight = dist_recip / norm
-            interpolated_feats = ops.three_interpolate(known_feats, idx, weight)
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        """unknown (B,n,3), known (B,m,3) | None, unknow_feats (B,C1,n) | None, known_feats (B,C2,m) -> (B, mlp[-1], n)"""
+        if known is None:  # a GroupAll level above: its single feature column is broadcast to every point
+            carried = known_feats.expand(known_feats.size(0), known_feats.size(1), unknown.size(1))
         else:
-            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
-
-        if unknow_feats is not None:
-            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
-        else:
-            new_features = interpolated_feats
-        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+            dist, nearest = self._ops.three_nn(unknown, known)
+            inv = 1.0 / (dist + 1e-8)                                   # pointnet2_modules.py:157-159
+            carried = self._ops.three_interpolate(known_feats, nearest, inv / inv.sum(dim=2, keepdim=True))
+        stacked = carried if unknow_feats is None else torch.cat([carried, unknow_feats], dim=1)
+        return self.mlp(stacked.unsqueeze(-1)).squeeze(-1)

@@ -1,14 +1,15 @@
-"""Python op surface: the six autograd Functions plus QueryAndGroup / GroupAll of the reference's
-pointnet2_lib/pointnet2/pointnet2_utils.py (same names, argument order and return values), running on
-the B200 kernels of libepnet_b200.so.
+"""Python op surface of pointnet2_lib/pointnet2/pointnet2_utils.py on the B200 kernels: the six autograd ops
+(FurthestPointSampling, GatherOperation, ThreeNN, ThreeInterpolate, GroupingOperation, BallQuery and their lower-case
+`.apply` aliases) plus the QueryAndGroup / GroupAll modules -- same names, argument order and return values.
 
-The Functions are produced by `make_ops(backend)` where `backend` is any module exposing the nine
-`*_wrapper` functions of the reference's pybind table; the module-level names below are bound to
-epnet_b200.pointnet2_cuda.  tests/ and bench.py's reference arm build a second set on the reference's
-own kernels (oracle/ref_cuda.py) through the same factory -- the product never does.
+Design: every op is described once by a pair of plain functions (launch, optional gradient launch) that receive a backend
+module exposing the nine `*_wrapper` entry points of the reference's pybind table; `make_ops(backend)` turns the table into
+`torch.autograd.Function` classes.  The module-level names are bound to epnet_b200.pointnet2_cuda (libepnet_b200.so);
+tests/ and bench.py's reference arm build a second set on the reference's own kernels through the same table -- the product
+never does.  Buffers the reference expects pre-filled (FPS scratch 1e10, zeroed ball-query indices, zeroed gradients) are
+prepared here, exactly where the reference's Python layer prepares them (pointnet2_utils.py:26, :218, :67/:146/:190).
 """
 from types import SimpleNamespace
-from typing import Tuple
 
 import torch
 import torch.nn as nn
@@ -17,188 +18,175 @@ from torch.autograd import Function
 from . import pointnet2_cuda as _default_backend
 
 
+def _buf(like, *shape, dtype=torch.float32, fill=None):
+    """output / scratch tensor on `like`'s device; fill=None leaves it uninitialised"""
+    if fill is None:
+        return torch.empty(shape, dtype=dtype, device=like.device)
+    return torch.full(shape, fill, dtype=dtype, device=like.device)
+
+
+def _dense(*tensors):
+    for t in tensors:
+        assert t.is_contiguous(), "pointnet2 ops take contiguous tensors (as the reference asserts)"
+
+
+# ---- op table: name -> (forward launch, gradient launch or None, number of forward arguments) -------------------------
+# forward(be, ctx, *args) returns the op's outputs; it may stash what the gradient needs on ctx.saved
+# gradient(be, ctx, *grads) returns the gradient w.r.t. the FIRST forward argument (the only differentiable one)
+
+def _fps(be, ctx, cloud, count):  # (B,N,3) -> (B,count) int32 sample indices, bit-exact (pointnet2_utils.py:12-29)
+    _dense(cloud)
+    scenes, n = cloud.shape[0], cloud.shape[1]
+    picked = _buf(cloud, scenes, count, dtype=torch.int32)
+    be.furthest_point_sampling_wrapper(scenes, n, count, cloud, _buf(cloud, scenes, n, fill=1e10), picked)
+    ctx.mark_non_differentiable(picked)
+    return picked
+
+
+def _gather(be, ctx, feats, which):  # (B,C,N), (B,M) -> (B,C,M)   (pointnet2_utils.py:42-63)
+    _dense(feats, which)
+    scenes, chans, n = feats.shape
+    m = which.shape[1]
+    ctx.saved = (which, chans, n)
+    picked = _buf(feats, scenes, chans, m)
+    be.gather_points_wrapper(scenes, chans, n, m, feats, which, picked)
+    return picked
+
+
+def _gather_grad(be, ctx, g):  # scatter-add back (pointnet2_utils.py:65-73)
+    which, chans, n = ctx.saved
+    scenes, m = which.shape
+    acc = _buf(g, scenes, chans, n, fill=0.0)
+    be.gather_points_grad_wrapper(scenes, chans, n, m, g.contiguous(), which, acc)
+    return acc
+
+
+def _nn3(be, ctx, queries, anchors):  # -> (distances (B,n,3), indices (B,n,3))   (pointnet2_utils.py:79-98)
+    _dense(queries, anchors)
+    scenes, n = queries.shape[0], queries.shape[1]
+    sq = _buf(queries, scenes, n, 3)
+    which = _buf(queries, scenes, n, 3, dtype=torch.int32)
+    be.three_nn_wrapper(scenes, n, anchors.shape[1], queries, anchors, sq, which)
+    ctx.mark_non_differentiable(which)
+    return sq.sqrt(), which  # the kernel returns squared distances; the reference takes the root in Python too (:98)
+
+
+def _interp(be, ctx, feats, which, w):  # (B,C,m), (B,n,3) x2 -> (B,C,n)   (pointnet2_utils.py:111-131)
+    _dense(feats, which, w)
+    scenes, chans, m = feats.shape
+    n = which.shape[1]
+    ctx.saved = (which, w, m)
+    mixed = _buf(feats, scenes, chans, n)
+    be.three_interpolate_wrapper(scenes, chans, m, n, feats, which, w, mixed)
+    return mixed
+
+
+def _interp_grad(be, ctx, g):  # (pointnet2_utils.py:133-153)
+    which, w, m = ctx.saved
+    scenes, chans, n = g.shape
+    acc = _buf(g, scenes, chans, m, fill=0.0)
+    be.three_interpolate_grad_wrapper(scenes, chans, n, m, g.contiguous(), which, w, acc)
+    return acc
+
+
+def _group(be, ctx, feats, which):  # (B,C,N), (B,M,S) -> (B,C,M,S)   (pointnet2_utils.py:159-179)
+    _dense(feats, which)
+    scenes, chans, n = feats.shape
+    m, s = which.shape[1], which.shape[2]
+    ctx.saved = (which, n)
+    grouped = _buf(feats, scenes, chans, m, s)
+    be.group_points_wrapper(scenes, chans, n, m, s, feats, which, grouped)
+    return grouped
+
+
+def _group_grad(be, ctx, g):  # (pointnet2_utils.py:181-197)
+    which, n = ctx.saved
+    scenes, chans, m, s = g.shape
+    acc = _buf(g, scenes, chans, n, fill=0.0)
+    be.group_points_grad_wrapper(scenes, chans, n, m, s, g.contiguous(), which, acc)
+    return acc
+
+
+def _ball(be, ctx, radius, per_ball, cloud, centres):  # -> (B,M,per_ball) int32, reference padding rule (pointnet2_utils.py:203-221)
+    _dense(centres, cloud)
+    scenes, n, m = cloud.shape[0], cloud.shape[1], centres.shape[1]
+    members = _buf(cloud, scenes, m, per_ball, dtype=torch.int32, fill=0)  # an empty ball keeps these zeros
+    be.ball_query_wrapper(scenes, n, m, radius, per_ball, centres, cloud, members)
+    ctx.mark_non_differentiable(members)
+    return members
+
+
+_TABLE = {
+    "FurthestPointSampling": (_fps, None, 2),
+    "GatherOperation": (_gather, _gather_grad, 2),
+    "ThreeNN": (_nn3, None, 2),
+    "ThreeInterpolate": (_interp, _interp_grad, 3),
+    "GroupingOperation": (_group, _group_grad, 2),
+    "BallQuery": (_ball, None, 4),
+}
+_ALIASES = {"FurthestPointSampling": "furthest_point_sample", "GatherOperation": "gather_operation", "ThreeNN": "three_nn",
+            "ThreeInterpolate": "three_interpolate", "GroupingOperation": "grouping_operation", "BallQuery": "ball_query"}
+
+
+def _function_class(name, backend, launch, grad, arity):
+    def forward(ctx, *args):
+        return launch(backend, ctx, *args)
+
+    def backward(ctx, *grads):
+        first = grad(backend, ctx, grads[0]) if grad is not None else None
+        return (first,) + (None,) * (arity - 1)
+
+    return type(name, (Function,), {"forward": staticmethod(forward), "backward": staticmethod(backward),
+                                    "__doc__": "%s of pointnet2_utils.py on backend %s" % (name, getattr(backend, "__name__", backend))})
+
+
 def make_ops(backend):
-    """Build the op set of pointnet2_utils.py on `backend` (reference line numbers in each docstring)."""
-
-    class FurthestPointSampling(Function):
-        @staticmethod
-        def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
-            """pointnet2_utils.py:12-29.  xyz (B,N,3) -> (B,npoint) int32 indices; bit-exact."""
-            assert xyz.is_contiguous()
-            B, N, _ = xyz.size()
-            output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-            temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-            backend.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, output)
-            ctx.mark_non_differentiable(output)
-            return output
-
-        @staticmethod
-        def backward(ctx, a=None):
-            return None, None
-
-    class GatherOperation(Function):
-        @staticmethod
-        def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-            """pointnet2_utils.py:42-63.  features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
-            assert features.is_contiguous()
-            assert idx.is_contiguous()
-            B, npoint = idx.size()
-            _, C, N = features.size()
-            output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-            backend.gather_points_wrapper(B, C, N, npoint, features, idx, output)
-            ctx.for_backwards = (idx, C, N)
-            return output
-
-        @staticmethod
-        def backward(ctx, grad_out):
-            idx, C, N = ctx.for_backwards
-            B, npoint = idx.size()
-            grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-            backend.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad_features)
-            return grad_features, None
-
-    class ThreeNN(Function):
-        @staticmethod
-        def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-            """pointnet2_utils.py:79-98.  Returns (sqrt of the 3 smallest squared distances, their indices)."""
-            assert unknown.is_contiguous()
-            assert known.is_contiguous()
-            B, N, _ = unknown.size()
-            m = known.size(1)
-            dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
-            idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-            backend.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
-            ctx.mark_non_differentiable(idx)
-            return torch.sqrt(dist2), idx
-
-        @staticmethod
-        def backward(ctx, a=None, b=None):
-            return None, None
-
-    class ThreeInterpolate(Function):
-        @staticmethod
-        def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-            """pointnet2_utils.py:111-131.  features (B,C,m), idx/weight (B,n,3) -> (B,C,n)."""
-            assert features.is_contiguous()
-            assert idx.is_contiguous()
-            assert weight.is_contiguous()
-            B, c, m = features.size()
-            n = idx.size(1)
-            ctx.three_interpolate_for_backward = (idx, weight, m)
-            output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-            backend.three_interpolate_wrapper(B, c, m, n, features, idx, weight, output)
-            return output
-
-        @staticmethod
-        def backward(ctx, grad_out: torch.Tensor):
-            idx, weight, m = ctx.three_interpolate_for_backward
-            B, c, n = grad_out.size()
-            grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-            backend.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
-            return grad_features, None, None
-
-    class GroupingOperation(Function):
-        @staticmethod
-        def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-            """pointnet2_utils.py:159-179.  features (B,C,N), idx (B,npoint,nsample) -> (B,C,npoint,nsample)."""
-            assert features.is_contiguous()
-            assert idx.is_contiguous()
-            B, nfeatures, nsample = idx.size()
-            _, C, N = features.size()
-            output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-            backend.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, output)
-            ctx.for_backwards = (idx, N)
-            return output
-
-        @staticmethod
-        def backward(ctx, grad_out: torch.Tensor):
-            idx, N = ctx.for_backwards
-            B, C, npoint, nsample = grad_out.size()
-            grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-            backend.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
-            return grad_features, None
-
-    class BallQuery(Function):
-        @staticmethod
-        def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-            """pointnet2_utils.py:203-221.  -> (B,npoint,nsample) int32, bit-exact incl. padding order."""
-            assert new_xyz.is_contiguous()
-            assert xyz.is_contiguous()
-            B, N, _ = xyz.size()
-            npoint = new_xyz.size(1)
-            idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-            backend.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
-            ctx.mark_non_differentiable(idx)
-            return idx
-
-        @staticmethod
-        def backward(ctx, a=None):
-            return None, None, None, None
-
-    ops = SimpleNamespace(
-        backend=backend,
-        FurthestPointSampling=FurthestPointSampling, furthest_point_sample=FurthestPointSampling.apply,
-        GatherOperation=GatherOperation, gather_operation=GatherOperation.apply,
-        ThreeNN=ThreeNN, three_nn=ThreeNN.apply,
-        ThreeInterpolate=ThreeInterpolate, three_interpolate=ThreeInterpolate.apply,
-        GroupingOperation=GroupingOperation, grouping_operation=GroupingOperation.apply,
-        BallQuery=BallQuery, ball_query=BallQuery.apply,
-    )
+    """The op set on `backend`: namespace with the six Function classes, their `.apply` aliases and `.backend`."""
+    ops = SimpleNamespace(backend=backend)
+    for name, (launch, grad, arity) in _TABLE.items():
+        cls = _function_class(name, backend, launch, grad, arity)
+        setattr(ops, name, cls)
+        setattr(ops, _ALIASES[name], cls.apply)
     return ops
 
 
 OPS = make_ops(_default_backend)
-
-FurthestPointSampling = OPS.FurthestPointSampling
-furthest_point_sample = OPS.furthest_point_sample
-GatherOperation = OPS.GatherOperation
-gather_operation = OPS.gather_operation
-ThreeNN = OPS.ThreeNN
-three_nn = OPS.three_nn
-ThreeInterpolate = OPS.ThreeInterpolate
-three_interpolate = OPS.three_interpolate
-GroupingOperation = OPS.GroupingOperation
-grouping_operation = OPS.grouping_operation
-BallQuery = OPS.BallQuery
-ball_query = OPS.ball_query
+for _name in _TABLE:  # module-level names, as the reference exposes them
+    globals()[_name] = getattr(OPS, _name)
+    globals()[_ALIASES[_name]] = getattr(OPS, _ALIASES[_name])
+del _name
 
 
 class QueryAndGroup(nn.Module):
-    """pointnet2_utils.py:231-264: ball query, group xyz (re-centred on the query) and features."""
+    """Ball query around every centre, then the members' coordinates (relative to the centre) and features, stacked on the
+    channel axis (pointnet2_utils.py:231-264).  cloud (B,N,3), centres (B,M,3), feats (B,C,N) -> (B, 3+C, M, nsample)."""
 
-    def __init__(self, radius: float, nsample: int, use_xyz: bool = True, ops=None):
+    def __init__(self, radius, nsample, use_xyz=True, ops=None):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
         self._ops = ops or OPS
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None) -> torch.Tensor:
-        """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) -> (B,3+C,npoint,nsample)."""
+    def forward(self, xyz, new_xyz, features=None):
         ops = self._ops
-        idx = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = ops.grouping_operation(xyz_trans, idx)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
-        if features is not None:
-            grouped_features = ops.grouping_operation(features, idx)
-            if self.use_xyz:
-                return torch.cat([grouped_xyz, grouped_features], dim=1)
-            return grouped_features
-        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-        return grouped_xyz
+        members = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
+        offsets = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), members) - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is None:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+            return offsets
+        picked = ops.grouping_operation(features, members)
+        return torch.cat([offsets, picked], dim=1) if self.use_xyz else picked
 
 
 class GroupAll(nn.Module):
-    """pointnet2_utils.py:267-290: a single group holding every point."""
+    """One group holding the whole cloud (pointnet2_utils.py:267-290): (B,N,3), _, (B,C,N) -> (B, 3+C, 1, N)."""
 
-    def __init__(self, use_xyz: bool = True, ops=None):
+    def __init__(self, use_xyz=True, ops=None):
         super().__init__()
         self.use_xyz = use_xyz
 
-    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            if self.use_xyz:
-                return torch.cat([grouped_xyz, grouped_features], dim=1)
-            return grouped_features
-        return grouped_xyz
+    def forward(self, xyz, new_xyz, features=None):
+        coords = xyz.transpose(1, 2).unsqueeze(2)
+        if features is None:
+            return coords
+        feats = features.unsqueeze(2)
+        return torch.cat([coords, feats], dim=1) if self.use_xyz else feats
