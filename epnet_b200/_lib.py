@@ -26,6 +26,8 @@ SIGNATURES = {
     "epnet_grid_gather_bilinear_grad": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
     "epnet_fps_sample": [_c_int] * 3 + [_c_void_p] * 6 + [_c_int, _c_void_p],
     "epnet_group_concat": [_c_int] * 5 + [_c_void_p] * 6,
+    "epnet_attention_scale_pm": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
+                                 _c_void_p],
     "epnet_bias_relu": [_c_int, _c_int, _c_ll, _c_void_p, _c_void_p, _c_void_p],
     "epnet_bias_relu_maxpool": [_c_int] * 4 + [_c_void_p] * 3 + [_c_ll, _c_void_p],
     "epnet_three_interpolate_concat": [_c_int] * 5 + [_c_void_p] * 6,

@@ -552,3 +552,49 @@ EPNET_API int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, cons
     deconv_shuffle_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, w, k, co, y, out, ldo, col_off, total);
     EPNET_RETURN_LAUNCH_STATUS();
 }
+
+// LI-Fusion attention tail (IA_Layer.forward, lib/net/pointnet2_msg.py:79-96) on point-major rows, one pass:
+//   att = sigmoid(w3 . tanh(r1 + r2) + b3)        r1 = fc1(img) (+ both biases), r2 = fc2(point): (rows, rc)
+//   out[row][0..c) = x[row][0..c) * att            x = conv1(img) after BN+ReLU: (rows, c)
+// replacing the add / tanh / gemv / add / sigmoid / mul launches of the op-by-op version.  A warp per row; rc % 4 == c % 4 == 0.
+namespace epnet {
+__global__ void __launch_bounds__(256)
+attention_scale_pm_kernel(int rows, int rc, int c, const float *__restrict__ r1, int ld1, const float *__restrict__ r2, int ld2,
+                          const float *__restrict__ w3, const float *__restrict__ b3, const float *__restrict__ x, int ldx,
+                          float *__restrict__ out, int ldo)
+{
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4 *a = reinterpret_cast<const float4 *>(r1 + (size_t)row * ld1);
+    const float4 *b = reinterpret_cast<const float4 *>(r2 + (size_t)row * ld2);
+    const float4 *w = reinterpret_cast<const float4 *>(w3);
+    float dot = 0.f;
+    for (int j = lane; j < rc / 4; j += 32) {
+        const float4 p = __ldg(a + j), q = __ldg(b + j), ww = __ldg(w + j);
+        dot += ww.x * tanhf(p.x + q.x) + ww.y * tanhf(p.y + q.y) + ww.z * tanhf(p.z + q.z) + ww.w * tanhf(p.w + q.w);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float att = 1.0f / (1.0f + expf(-(dot + __ldg(b3))));
+    const float4 *xs = reinterpret_cast<const float4 *>(x + (size_t)row * ldx);
+    float4 *os = reinterpret_cast<float4 *>(out + (size_t)row * ldo);
+    for (int j = lane; j < c / 4; j += 32) {
+        const float4 v = __ldg(xs + j);
+        os[j] = make_float4(v.x * att, v.y * att, v.z * att, v.w * att);
+    }
+}
+}  // namespace epnet
+
+EPNET_API int epnet_attention_scale_pm(int rows, int rc, int c, const float *r1, int ld1, const float *r2, int ld2, const float *w3,
+                                       const float *b3, const float *x, int ldx, float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (rows < 0 || rc <= 0 || c <= 0 || !r1 || !r2 || !w3 || !b3 || !x || !out) return EPNET_ERR_BAD_ARG;
+    if ((rc & 3) || (c & 3) || (ld1 & 3) || (ld2 & 3) || (ldx & 3) || (ldo & 3) || ld1 < rc || ld2 < rc || ldx < c || ldo < c) return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(r1) | reinterpret_cast<uintptr_t>(r2) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(x) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return EPNET_ERR_BAD_ARG;
+    if (rows == 0) return EPNET_OK;
+    attention_scale_pm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rows, rc, c, r1, ld1, r2, ld2, w3, b3, x, ldx, out, ldo);
+    EPNET_RETURN_LAUNCH_STATUS();
+}

@@ -12,18 +12,20 @@ import torch
 from ._lib import LIB, check
 
 
-def _dev_ptr(t, dtype, name):
+def _dev_ptr(t, dtype, name, contiguous=True):
     if not t.is_cuda:
         raise ValueError("%s must be a CUDA tensor (epnet_b200 has no CPU path)" % name)
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
-    if not t.is_contiguous():
+    if contiguous and not t.is_contiguous():
         raise ValueError("%s must be contiguous" % name)
+    if not contiguous and t.stride(-1) != 1:
+        raise ValueError("%s must have unit stride along its last axis" % name)
     return t.data_ptr()
 
 
-def _f(t, name):
-    return _dev_ptr(t, torch.float32, name)
+def _f(t, name, contiguous=True):
+    return _dev_ptr(t, torch.float32, name, contiguous)
 
 
 def _i(t, name):
@@ -181,6 +183,14 @@ def fps_sample_wrapper(b, n, m, xyz, temp, idx, new_xyz=None, aux_in=None, aux_o
 def group_concat_wrapper(b, c, n, m, nsample, xyz, new_xyz, features, idx, out):
     _call("group_concat", LIB.epnet_group_concat, xyz, b, c, n, m, nsample, _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
           _opt(features, torch.float32, "features"), _i(idx, "idx"), _f(out, "out"))
+
+
+def attention_scale_pm_wrapper(r1, r2, w3, b3, x, out):
+    """out[row] = x[row] * sigmoid(w3 . tanh(r1[row] + r2[row]) + b3); r1, r2 (rows, rc), x, out (rows, c) row-major (strided ok)"""
+    rows, rc, c = r1.shape[0], r1.shape[1], x.shape[1]
+    _call("attention_scale_pm", LIB.epnet_attention_scale_pm, x, rows, rc, c, _f(r1, "r1", contiguous=False), r1.stride(0),
+          _f(r2, "r2", contiguous=False), r2.stride(0), _f(w3, "w3"), _f(b3, "b3"), _f(x, "x", contiguous=False), x.stride(0),
+          _f(out, "out", contiguous=False), out.stride(0))
 
 
 def bias_relu_wrapper(b, c, l, x, bias):

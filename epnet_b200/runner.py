@@ -84,7 +84,7 @@ class _FusionPM:
             ia = mod.IA_Layer
             self.fc1 = PackedLinear(ia.fc1.weight, ia.fc1.bias + ia.fc2.bias)  # the two biases are summed before tanh
             self.fc2 = PackedLinear(ia.fc2.weight, None)
-            self.w3, self.b3 = ia.fc3.weight.detach().reshape(-1).contiguous(), ia.fc3.bias.detach()
+            self.w3, self.b3 = ia.fc3.weight.detach().reshape(-1).contiguous(), ia.fc3.bias.detach().reshape(1).contiguous()
             conv, bn = ia.conv1[0], ia.conv1[1]
             self.conv = PackedLinear(*_fold_bn(conv.weight.squeeze(-1), conv.bias, bn))
         self.fuse = PackedLinear(*_fold_bn(mod.conv1.weight.squeeze(-1), mod.conv1.bias, mod.bn1))
@@ -96,10 +96,9 @@ class _FusionPM:
         cp = self.cp
         if self.attention:
             point = cat[:, :cp]
-            r = self.fc1(img, relu=False) + self.fc2(point, relu=False)
-            att = torch.sigmoid(torch.tanh(r) @ self.w3 + self.b3)  # (rows,)
-            img_new = self.conv(img, relu=True)
-            torch.mul(img_new, att[:, None], out=cat[:, cp:])
+            # att = sigmoid(fc3(tanh(fc1(img) + fc2(point)))) and the scaling of conv1(img) in one pass over the rows
+            pc.attention_scale_pm_wrapper(self.fc1(img, relu=False), self.fc2(point, relu=False), self.w3, self.b3,
+                                          self.conv(img, relu=True), cat[:, cp:])
         else:
             cat[:, cp:].copy_(img)
         return self.fuse(cat, relu=True, out=out)

@@ -153,6 +153,10 @@ int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride
  * (B,H,W,ldc) -> out[(b,i)][0..C).  deconv_shuffle_nhwc: the pixel shuffle of a ConvTranspose2d with kernel == stride
  * (pointnet2_msg.py:163-165,239-241) computed as a GEMM y (B*h*w, k*k*co) -> out (B, h*k, w*k, ldo)[..., col_off:col_off+co],
  * i.e. straight into the channel concat of :242. */
+/* LI-Fusion attention tail (IA_Layer.forward, lib/net/pointnet2_msg.py:79-96) on point-major rows in one pass:
+ * out[row] = x[row] * sigmoid(w3 . tanh(r1[row] + r2[row]) + b3), r1/r2 (rows, rc), x/out (rows, c); all 16-byte aligned. */
+int epnet_attention_scale_pm(int rows, int rc, int c, const float *r1, int ld1, const float *r2, int ld2, const float *w3,
+                             const float *b3, const float *x, int ldx, float *out, int ldo, void *stream);
 int epnet_grid_gather_nhwc_pm(int b, int c, int h, int w, int n, const float *fmap, int ldc, const float *xy, int align_corners,
                               float *out, int ldo, void *stream);
 int epnet_deconv_shuffle_nhwc(int b, int h, int w, int k, int co, const float *y, float *out, int ldo, int col_off, void *stream);

@@ -131,3 +131,24 @@ def test_deconv_as_gemm_plus_shuffle_equals_conv_transpose():
     assert (cat[..., :4] == 0).all() and (cat[..., 20:] == 0).all()
     err = (got - want).abs().max().item()
     assert err <= 5e-6 * want.abs().max().item(), err
+
+
+@pytest.mark.parametrize("rows,rc,c", [(8192, 24, 96), (2048, 64, 256), (130, 256, 1024), (32768, 8, 32), (5, 128, 512)])
+def test_attention_scale_pm(rows, rc, c):
+    """IA_Layer tail in one kernel == the op-by-op torch expression (lib/net/pointnet2_msg.py:88-95), written into a column
+    slice of a wider buffer."""
+    from epnet_b200 import pointnet2_cuda as pc
+    g = torch.Generator(device="cpu").manual_seed(rows + c)
+    r1 = torch.randn(rows, rc, generator=g).cuda()
+    r2 = torch.randn(rows, rc, generator=g).cuda()
+    w3 = (torch.randn(rc, generator=g) / rc ** 0.5).cuda()
+    b3 = torch.randn(1, generator=g).cuda()
+    x = torch.randn(rows, c, generator=g).cuda().relu()
+    cat = torch.full((rows, 2 * c + 4), -3.0, device="cuda")
+    pc.attention_scale_pm_wrapper(r1, r2, w3, b3, x, cat[:, c:2 * c])
+    torch.cuda.synchronize()
+    att = torch.sigmoid(torch.tanh(r1.double() + r2.double()) @ w3.double() + b3.double())
+    want = x.double() * att[:, None]
+    err = (cat[:, c:2 * c].double() - want).abs().max().item()
+    assert err <= 2e-6 * max(want.abs().max().item(), 1.0)
+    assert (cat[:, :c] == -3.0).all() and (cat[:, 2 * c:] == -3.0).all()
