@@ -108,6 +108,9 @@ struct GemmArgs {
     // n = (ky*dk + kx)*dco + o; the epilogue writes the dco channels to output pixel (yi*dk+ky, xi*dk+kx) of the NHWC buffer y
     // (pixel stride ldy) instead of to row-major (L, ldy).  dco % 4 == 0.
     int dk, dco;
+    // channel-major output: rows are (scene, point) pairs with `tr` points per scene and y is (scenes, N, tr) -- the interface
+    // layout (B, C, N) of the reference -- written straight from the epilogue (lanes = consecutive points: coalesced per column)
+    int tr;
 };
 
 // 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
@@ -247,7 +250,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
             if (a.relu) f = fmaxf(f, 0.f);
             v[j] = __float_as_uint(f);
         }
-        if (a.dk) {
+        if (a.tr) {
+            if (row < a.L) {
+                const int scene = row / a.tr, pt = row - scene * a.tr;
+                float *dst = a.y + ((size_t)scene * a.N + n0) * a.tr + pt;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols && n0 + j < a.N) dst[(size_t)j * a.tr] = __uint_as_float(v[j]);
+            }
+        } else if (a.dk) {
             if (row < a.L) {
                 const int byi = row / a.W, xi = row - byi * a.W;
                 const size_t wo = (size_t)a.W * a.dk;
@@ -736,6 +747,24 @@ EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, co
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
     a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
     a.relu = relu; a.pool = pool;
+    a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+    return gemm_launch(a, (cudaStream_t)stream);
+}
+
+// The same product with the result written channel-major: x rows are (scene, point) pairs, `pts` points per scene (L % pts == 0),
+// y is (L / pts, N, pts) -- the (B, C, N) layout the reference's modules exchange -- so the last layer of a point-major chain
+// needs no transposing pass.
+EPNET_API int epnet_gemm_tf32x3_cm(int L, int K, int N, int pts, const float *x, int ldx, const float *wpack, int BN, const float *bias,
+                                   int relu, float *y, void *stream)
+{
+    using namespace epnet;
+    if (L < 0 || K <= 0 || N <= 0 || pts <= 0 || (L % pts) != 0 || !x || !wpack || !y || ldx < K) return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || (reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (L == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
+    a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = N; a.BN = BN;
+    a.relu = relu; a.pool = 1; a.tr = pts;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
     return gemm_launch(a, (cudaStream_t)stream);
 }

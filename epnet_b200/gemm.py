@@ -89,13 +89,20 @@ class PackedLinear:
             bn = choose_bn(min(self.N, 128))
         return bn, self._pack(bn)
 
-    def __call__(self, x, relu=True, pool=1, out=None):
-        """x (..., K) point-major rows (last dim contiguous) -> (rows / pool, N)"""
+    def __call__(self, x, relu=True, pool=1, out=None, out_cm=None):
+        """x (..., K) point-major rows (last dim contiguous) -> (rows / pool, N); with out_cm (B, N, pts) contiguous the result
+        is written channel-major instead (rows = B * pts), straight from the epilogue."""
         assert x.is_cuda and x.dtype == torch.float32 and x.stride(-1) == 1
         x2 = x.reshape(-1, x.shape[-1]) if x.is_contiguous() else x
         assert x2.dim() == 2
         L, ldx = x2.shape[0], x2.stride(0)
         assert x2.shape[1] >= self.K
+        if out_cm is not None:
+            assert pool == 1 and out_cm.is_contiguous() and out_cm.shape[1] == self.N and out_cm.shape[0] * out_cm.shape[2] == L
+            bn, wpack = self.for_rows(L)
+            pc._call("gemm_tf32x3_cm", LIB.epnet_gemm_tf32x3_cm, x2, L, self.K, self.N, out_cm.shape[2], x2.data_ptr(), ldx, wpack.data_ptr(),
+                     bn, None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), out_cm.data_ptr())
+            return out_cm
         if out is None:
             out = torch.empty((L // pool, self.N), dtype=torch.float32, device=x.device)
         assert out.stride(-1) == 1

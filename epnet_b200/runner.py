@@ -91,8 +91,9 @@ class _FusionPM:
         self.cp = mod.conv1.out_channels
         self.cat_width = mod.conv1.in_channels
 
-    def __call__(self, cat, img, out=None):
-        """cat (rows, Cp + Ci') with point features in [:, :Cp]; img (rows, Ci) gathered image features -> (rows, Cp)"""
+    def __call__(self, cat, img, out=None, out_cm=None):
+        """cat (rows, Cp + Ci') with point features in [:, :Cp]; img (rows, Ci) gathered image features -> (rows, Cp), or
+        channel-major into out_cm (B, Cp, pts)"""
         cp = self.cp
         if self.attention:
             point = cat[:, :cp]
@@ -101,7 +102,7 @@ class _FusionPM:
                                           self.conv(img, relu=True), cat[:, cp:])
         else:
             cat[:, cp:].copy_(img)
-        return self.fuse(cat, relu=True, out=out)
+        return self.fuse(cat, relu=True, out=out, out_cm=out_cm)
 
 class BackboneRunner:
     def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency"):
@@ -470,7 +471,8 @@ class BackboneRunner:
             ci = img_fusion.shape[3]  # NHWC
             g = torch.empty((B * N, ci), **f32)
             pc.grid_gather_nhwc_pm_wrapper(B, ci, img_fusion.shape[1], img_fusion.shape[2], N, img_fusion, xyn, c.align_corners, g)
-            feats = self.final_fusion_pm(final_cat, g)
+            # the last GEMM writes the interface layout (B, C, N) itself: no transposing pass
+            return self.final_fusion_pm(final_cat, g, out_cm=torch.empty((B, self.final_fusion_pm.cp, N), **f32))
         return feats.view(B, N, -1).transpose(1, 2).contiguous()  # interface layout (B, C, N)
 
     # ------------------------------------------------------------------------------------ graph

@@ -143,6 +143,11 @@ int epnet_three_nn_weights(int b, int n, int m, const float *unknown, const floa
 int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, int ldo,
                          void *stream);
 
+/* epnet_gemm_tf32x3 with the result written channel-major: x rows are (scene, point) pairs, `pts` points per scene, y is
+ * (L/pts, N, pts), i.e. the (B, C, N) feature layout of the reference's modules (pointnet2_modules.py:72). */
+int epnet_gemm_tf32x3_cm(int L, int K, int N, int pts, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
+                         float *y, void *stream);
+
 /* 3x3 convolution (padding 1, stride 1 or 2) as an implicit tcgen05 3xTF32 GEMM on an NHWC image -- the image-stream
  * convolutions of BasicBlock (lib/net/pointnet2_msg.py:17-33; cuDNN fp32 there).  x (B,H,W,Cin), Cin a power of two >= 4;
  * wpack = the weight reordered to (Cout, ky, kx, Cin) and packed like epnet_gemm_tf32x3's; y (B*Ho*Wo, ldy) NHWC. */

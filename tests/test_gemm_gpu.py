@@ -118,3 +118,17 @@ def test_deconv_nhwc_matches_fp64(B, h, w, cin, cpad, k, co):
     err = (cat[..., 8:8 + co].double() - want).abs().max().item()
     assert err <= 4e-6 * want.abs().max().item()
     assert (cat[..., :8] == 7.0).all() and (cat[..., 8 + co:] == 7.0).all()  # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("B,pts,K,N", [(2, 16384, 160, 128), (3, 1000, 70, 48), (1, 130, 300, 512)])
+def test_gemm_channel_major_output(B, pts, K, N):
+    """the epilogue can write (B, N, pts) -- the reference's (B, C, N) feature layout -- directly"""
+    from epnet_b200.gemm import PackedLinear
+    g = torch.Generator(device="cpu").manual_seed(pts + K)
+    x = torch.randn(B * pts, K, generator=g).cuda()
+    lin = PackedLinear((torch.randn(N, K, generator=g) / K ** 0.5).cuda(), torch.randn(N, generator=g).cuda())
+    out = torch.empty(B, N, pts, device="cuda")
+    lin(x, relu=True, out_cm=out)
+    torch.cuda.synchronize()
+    want = _ref(x, lin._w, lin.bias, True, 1).view(B, pts, N).transpose(1, 2)
+    assert (out.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
