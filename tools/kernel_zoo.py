@@ -25,6 +25,10 @@ for _ in range(reps):
     for r, ns in ((0.1, 16), (0.5, 32)):
         bidx = torch.zeros(B, 4096, ns, dtype=torch.int32, device=dev)
         pc.ball_query_wrapper(B, 16384, 4096, r, ns, new_xyz, pts, bidx)
+    buckets = pc.bucket_cloud(pts)  # Morton sort + 64-point boxes, then the same two queries through the buckets
+    for r, ns in ((0.1, 16), (0.5, 32)):
+        bidx = torch.zeros(B, 4096, ns, dtype=torch.int32, device=dev)
+        pc.ball_query_sorted_wrapper(B, 4096, r, ns, new_xyz, buckets, bidx)
     d2 = torch.empty(B, 16384, 3, device=dev)
     i3 = torch.empty(B, 16384, 3, dtype=torch.int32, device=dev)
     pc.three_nn_wrapper(B, 16384, 4096, pts, new_xyz, d2, i3)
@@ -80,6 +84,11 @@ for _ in range(reps):
     ydec = torch.randn(2 * 96 * 320, 4 * 4 * 16, device=dev)
     cat = torch.empty(2, 384, 1280, 64, device=dev)
     pc.deconv_shuffle_nhwc_wrapper(2, 96, 320, 4, 16, ydec, cat, 16)
+    # --- LI-Fusion attention tail at the SA1 level (8192 rows, rc = 24, c = 96) and the warp-per-scene FPS at RCNN shapes
+    pc.attention_scale_pm_wrapper(torch.randn(8192, 24, device=dev), torch.randn(8192, 24, device=dev), torch.randn(24, device=dev),
+                                  torch.zeros(1, device=dev), torch.randn(8192, 96, device=dev), torch.empty(8192, 96, device=dev))
+    roi = torch.randn(200, 512, 3, device=dev)
+    pc.furthest_point_sampling_wrapper(200, 512, 128, roi, torch.full((200, 512), 1e10, device=dev), torch.empty(200, 128, dtype=torch.int32, device=dev))
     # --- RoI pooling and the cluster (DSMEM) FPS at N = 131072
     boxes = torch.zeros(2, 64, 7, device=dev)
     boxes[..., 0] = torch.linspace(-20, 20, 64, device=dev); boxes[..., 1] = 1.8; boxes[..., 2] = torch.linspace(5, 60, 64, device=dev)
