@@ -111,6 +111,14 @@ struct GemmArgs {
     // channel-major output: rows are (scene, point) pairs with `tr` points per scene and y is (scenes, N, tr) -- the interface
     // layout (B, C, N) of the reference -- written straight from the epilogue (lanes = consecutive points: coalesced per column)
     int tr;
+    // grouped-gather A operand (first shared-MLP layer of a set-abstraction scale; narrow-tile kernel only): GEMM row r is the
+    // (scene, centre, sample) triple r, its columns are [feats[scene, g_idx[r], 0..g_c) | xyz[scene, g_idx[r]] - centre | 0...]:
+    // the grouped tensor of QueryAndGroup (pointnet2_utils.py:241-264) is never materialised.  x = feats (point-major rows of
+    // ldx floats, NULL when g_c == 0), K = g_c + 3, kcopy = g_c columns come from x.
+    const int *g_idx;
+    const float *g_xyz, *g_centre;
+    int g_n, g_ns, g_rows_scene;
+    int kcopy;             // columns of a row that are read from x (== K unless grouped)
 };
 
 // 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
@@ -155,6 +163,14 @@ struct RowSource {
                 while (xo >= a.Wo) { xo -= a.Wo; ++yo; }
                 while (yo >= a.Ho) { yo -= a.Ho; ++b; }
             }
+        } else if (a.g_idx) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = first + step * i;
+                const bool ok = row < a.L && a.kcopy > 0;
+                rmask[i] = ok ? 1u : 0u;
+                rowp[i] = ok ? a.x + ((size_t)(row / a.g_rows_scene) * a.g_n + __ldg(a.g_idx + row)) * a.ldx : a.x;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -182,15 +198,15 @@ struct RowSource {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rmask[i] && k0 < a.K) {
+            if (rmask[i] && k0 < a.kcopy) {
                 const float *src = rowp[i] + k0;
-                if (a.x_vec_ok && k0 + 4 <= a.K) {
+                if (a.x_vec_ok && k0 + 4 <= a.kcopy) {
                     v[i] = __ldg(reinterpret_cast<const float4 *>(src));
                 } else {
                     v[i].x = __ldg(src + 0);
-                    if (k0 + 1 < a.K) v[i].y = __ldg(src + 1);
-                    if (k0 + 2 < a.K) v[i].z = __ldg(src + 2);
-                    if (k0 + 3 < a.K) v[i].w = __ldg(src + 3);
+                    if (k0 + 1 < a.kcopy) v[i].y = __ldg(src + 1);
+                    if (k0 + 2 < a.kcopy) v[i].z = __ldg(src + 2);
+                    if (k0 + 3 < a.kcopy) v[i].w = __ldg(src + 3);
                 }
             }
         }
@@ -207,16 +223,16 @@ struct RowSource {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool ok = (rmask[i] >> tap) & 1u;
-                cp_async16_ca(base + dst_off[i], ok ? rowp[i] + off : a.x, ok ? 16u : 0u);  // neighbouring pixels share taps: keep L1
+                cp_async16_ca(base + dst_off[i], ok ? rowp[i] + off : a.wpack, ok ? 16u : 0u);  // neighbouring pixels share taps: keep L1
             }
             return;
         }
         if (a.x_vec_ok) {
-            const int valid = min(4, a.K - k0);  // floats of this chunk inside K (<= 0: none)
+            const int valid = min(4, a.kcopy - k0);  // floats of this chunk that exist in x (<= 0: none)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const bool ok = rmask[i] && valid > 0;
-                cp_async16_cg(base + dst_off[i], ok ? rowp[i] + k0 : a.x, ok ? (uint32_t)valid * 4u : 0u);
+                cp_async16_cg(base + dst_off[i], ok ? rowp[i] + k0 : a.wpack, ok ? (uint32_t)valid * 4u : 0u);  // wpack: a valid dummy address
             }
             return;
         }
@@ -591,6 +607,17 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
         for (int mt = blockIdx.x, it = 0; mt < m_tiles; mt += gridDim.x, ++it) {
         const int row0 = mt * kGmBM;
         int slot = 0;
+        // grouped operand: this lane's row gets three computed columns, the sample's offset from its centre
+        float goff[3] = {0.f, 0.f, 0.f};
+        if (a.g_idx) {
+            const int row = row0 + 32 * warp + lane;
+            if (row < a.L) {
+                const float *pp = a.g_xyz + ((size_t)(row / a.g_rows_scene) * a.g_n + __ldg(a.g_idx + row)) * 3;
+                const float *cc = a.g_centre + (size_t)(row / a.g_ns) * 3;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) goff[j] = __fsub_rn(__ldg(pp + j), __ldg(cc + j));  // as pointnet2_utils.py:252
+            }
+        }
         for (int kb = 0; kb < a.n_kblocks; ++kb) {
             // k-block kb has landed when at most depth-1 newer groups are pending
             if (a.depth == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -605,6 +632,15 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
                 v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
             }
             __syncwarp();  // the slot has been read by all lanes: refill it
+            if (a.g_idx && (kb + 1) * kGmBK > a.kcopy && kb * kGmBK < a.kcopy + 3) {  // this k-block holds offset columns
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int col = a.kcopy + j - kb * kGmBK;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (e == col) v[e] = __float_as_uint(goff[j]);
+                }
+            }
             if (kb + a.depth < a.n_kblocks) src.copy_async(a, (kb + a.depth) * kGmBK + chunk * 4, ring + slot * 4096, st_off);
             asm volatile("cp.async.commit_group;" ::: "memory");
             mbar_wait(&empty_a[t], ph ^ 1u);
@@ -694,6 +730,7 @@ namespace epnet {
 static int gemm_launch(GemmArgs &a, cudaStream_t st)
 {
     a.n_kblocks = (a.K + kGmBK - 1) / kGmBK;
+    if (!a.g_idx) a.kcopy = a.K;
     const int n_tiles = (a.N + a.BN - 1) / a.BN;
     dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
     // the opt-in shared-memory limit is a property of the function, not of a launch: always raise it to the hardware maximum so
@@ -748,6 +785,29 @@ EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, co
     a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
     a.relu = relu; a.pool = pool;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+    return gemm_launch(a, (cudaStream_t)stream);
+}
+
+// First shared-MLP layer of a set-abstraction scale with the grouping fused into the operand load (QueryAndGroup + Conv2d 1x1 +
+// BN + ReLU of pointnet2_modules.py:47-52): row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], :c] | xyz[scene, idx] -
+// new_xyz[scene, p]], never written to memory.  feats point-major (scenes, n, ldf) or NULL when c == 0; BN <= 64.
+EPNET_API int epnet_gemm_tf32x3_grouped(int scenes, int n, int m, int nsample, int c, const float *feats, int ldf, const float *xyz,
+                                        const float *new_xyz, const int *idx, const float *wpack, int BN, int N, const float *bias,
+                                        int relu, int pool, float *y, int ldy, void *stream)
+{
+    using namespace epnet;
+    if (scenes < 0 || n <= 0 || m < 0 || nsample <= 0 || c < 0 || (c > 0 && (!feats || ldf < c)) || !xyz || !new_xyz || !idx || !wpack || !y)
+        return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 64 || (BN % 16) != 0 || N <= 0 || ldy < N || (reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)scenes * m * nsample;
+    if (rows >= (1ll << 31) || pool < 1 || pool > 32 || (32 % pool) != 0 || (rows % pool) != 0) return EPNET_ERR_BAD_ARG;
+    if (rows == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.x = feats; a.wpack = wpack; a.bias = bias; a.y = y;
+    a.L = (int)rows; a.K = c + 3; a.N = N; a.ldx = ldf; a.ldy = ldy; a.BN = BN;
+    a.relu = relu; a.pool = pool;
+    a.g_idx = idx; a.g_xyz = xyz; a.g_centre = new_xyz; a.g_n = n; a.g_ns = nsample; a.g_rows_scene = m * nsample; a.kcopy = c;
+    a.x_vec_ok = c > 0 && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && (ldf % 4 == 0);
     return gemm_launch(a, (cudaStream_t)stream);
 }
 

@@ -113,6 +113,26 @@ class PackedLinear:
         return out
 
 
+def grouped_first_layer(lin, xyz, new_xyz, feats_pm, idx, relu=True, pool=1, out=None):
+    """lin(group(xyz, new_xyz, feats, idx)) without the grouped tensor: lin = PackedLinear over [features (C) | offsets (3)];
+    xyz (B,n,3), new_xyz (B,m,3), feats_pm (B,n,C) point-major or None, idx (B,m,ns) -> (B*m*ns / pool, N).
+    Returns None when this layer cannot take the fused path (column tile wider than 64): the caller groups explicitly."""
+    B, n = xyz.shape[0], xyz.shape[1]
+    m, ns = idx.shape[1], idx.shape[2]
+    c = 0 if feats_pm is None else feats_pm.shape[-1]
+    assert lin.K == c + 3
+    rows = B * m * ns
+    bn, wpack = lin.for_rows(rows)
+    if bn > 64:
+        return None
+    if out is None:
+        out = torch.empty((rows // pool, lin.N), dtype=torch.float32, device=xyz.device)
+    pc._call("gemm_tf32x3_grouped", LIB.epnet_gemm_tf32x3_grouped, xyz, B, n, m, ns, c, None if feats_pm is None else feats_pm.data_ptr(),
+             0 if feats_pm is None else feats_pm.stride(-2), xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), wpack.data_ptr(), bn, lin.N,
+             None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), pool, out.data_ptr(), out.stride(0))
+    return out
+
+
 class PackedDeconv:
     """ConvTranspose2d with kernel == stride on NHWC activations: one GEMM per map whose epilogue writes each input pixel's
     k x k x Cout patch into the output image (csrc/gemm_tf32x3.cu, dk mode).  weight (Cin, Cout, k, k) [+ bias (Cout)]."""

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
-from .gemm import PackedConv3x3, PackedDeconv, PackedLinear, tile_policy
+from .gemm import PackedConv3x3, PackedDeconv, PackedLinear, grouped_first_layer, tile_policy
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -423,10 +423,16 @@ class BackboneRunner:
                     else:  # more than two scales: query here
                         bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
                         pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
-                    kp = (cin + 3 + 3) // 4 * 4
-                    x = torch.empty((B * npoint * ns, kp), **f32)
-                    pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, None if feats is None else feats.view(B, n, cin), bidx, x)
-                    for lin in lins[:-1]:
+                    fpm = None if feats is None else feats.view(B, n, cin)
+                    # first layer: the grouped rows go from the feature table straight into the tensor-core operand
+                    x = grouped_first_layer(lins[0], xyz, new_xyz, fpm, bidx, relu=True) if len(lins) > 1 else None
+                    rest = lins[1:-1]
+                    if x is None:  # column tile wider than 64 (or a one-layer MLP): materialise the grouped rows
+                        kp = (cin + 3 + 3) // 4 * 4
+                        x = torch.empty((B * npoint * ns, kp), **f32)
+                        pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, fpm, bidx, x)
+                        rest = lins[:-1]
+                    for lin in rest:
                         x = lin(x, relu=True)
                     lins[-1](x, relu=True, pool=ns, out=cat[:, c_off:c_off + lins[-1].N])  # ReLU + max over nsample in the epilogue
                     if st is not main:

@@ -143,6 +143,14 @@ int epnet_three_nn_weights(int b, int n, int m, const float *unknown, const floa
 int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, int ldo,
                          void *stream);
 
+/* First shared-MLP layer of a set-abstraction scale with QueryAndGroup fused into the operand load (pointnet2_utils.py:241-264 +
+ * pointnet2_modules.py:47-52): GEMM row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], 0..c) | xyz[scene, idx] -
+ * new_xyz[scene, p]] is gathered straight into the tensor-core operand, the grouped tensor is never written.  feats point-major
+ * (scenes, n, ldf) or NULL when c == 0; wpack packs W (N, c+3) with the three offset columns LAST; BN <= 64. */
+int epnet_gemm_tf32x3_grouped(int scenes, int n, int m, int nsample, int c, const float *feats, int ldf, const float *xyz,
+                              const float *new_xyz, const int *idx, const float *wpack, int BN, int N, const float *bias, int relu,
+                              int pool, float *y, int ldy, void *stream);
+
 /* epnet_gemm_tf32x3 with the result written channel-major: x rows are (scene, point) pairs, `pts` points per scene, y is
  * (L/pts, N, pts), i.e. the (B, C, N) feature layout of the reference's modules (pointnet2_modules.py:72). */
 int epnet_gemm_tf32x3_cm(int L, int K, int N, int pts, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,

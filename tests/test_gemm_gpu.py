@@ -132,3 +132,30 @@ def test_gemm_channel_major_output(B, pts, K, N):
     torch.cuda.synchronize()
     want = _ref(x, lin._w, lin.bias, True, 1).view(B, pts, N).transpose(1, 2)
     assert (out.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("B,n,m,ns,c,N", [(2, 4096, 1024, 16, 96, 64), (2, 16384, 4096, 16, 0, 16), (1, 1000, 130, 32, 30, 48),
+                                          (2, 256, 64, 32, 512, 512), (3, 500, 77, 8, 5, 33)])
+def test_grouped_first_layer_equals_group_then_gemm(B, n, m, ns, c, N):
+    """QueryAndGroup fused into the GEMM operand == group_concat_pm followed by the plain GEMM, bit for bit (same values enter the
+    same MMAs), and both match the float64 reference; feature widths that are not multiples of 4 and an xyz-only level included."""
+    from epnet_b200 import pointnet2_cuda as pc
+    from epnet_b200.gemm import PackedLinear, grouped_first_layer
+    g = torch.Generator(device="cpu").manual_seed(n + c)
+    xyz = torch.randn(B, n, 3, generator=g).cuda()
+    new_xyz = xyz[:, :m].contiguous()
+    feats = None if c == 0 else torch.randn(B, n, c, generator=g).cuda()  # c % 4 != 0: rows are not 16-byte aligned
+    idx = torch.randint(0, n, (B, m, ns), generator=g).int().cuda()
+    lin = PackedLinear((torch.randn(N, c + 3, generator=g) / (c + 3) ** 0.5).cuda(), torch.randn(N, generator=g).cuda())
+    kp = (c + 3 + 3) // 4 * 4
+    rows = torch.empty(B * m * ns, kp, device="cuda")
+    pc.group_concat_pm_wrapper(B, c, n, m, ns, xyz, new_xyz, feats, idx, rows)
+    two_step = lin(rows, relu=True)
+    fused = grouped_first_layer(lin, xyz, new_xyz, feats, idx, relu=True)
+    torch.cuda.synchronize()
+    want = _ref(rows[:, :c + 3], lin._w, lin.bias, True, 1)
+    assert (two_step.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
+    if fused is None:
+        assert lin.for_rows(B * m * ns)[0] > 64  # wide tiles take the two-step path
+    else:
+        assert torch.equal(fused, two_step)
