@@ -211,6 +211,8 @@ def measure(model, runner, dev_pool, device, world):
         e["time"] += tot / reps
         e["launches"] += cnt // reps
         e["bytes"] += algorithmic_bytes(name, ints) * (cnt // reps)
+        if name in ("ball_query", "three_nn", "three_nn_weights"):  # exhaustive searches: (b, n, m, ...) -> b*n*m distance tests
+            e["tests"] = e.get("tests", 0.0) + float(ints[0]) * ints[1] * ints[2] * (cnt // reps)
         if name == "gemm_tf32x3":
             e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
         if name == "conv3x3_nhwc_tf32x3":  # (b, h, w, cin, cout, stride, BN, relu, ldy)
@@ -239,6 +241,8 @@ def measure(model, runner, dev_pool, device, world):
         else:
             row.update({"bound": "hbm", "achieved": round(e["bytes"] / e["time"] / 1e9, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(e["bytes"] / e["time"] / 1e9 / peak, 5)})
+        if e.get("tests"):  # the real bound of the search kernels is the fp32 distance-test rate, not bytes
+            row["distance_tests_per_s"] = round(e["tests"] / e["time"], -9)
         per_kernel.append(row)
     top = dict(per_kernel[0])
     traffic = None
