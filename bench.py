@@ -265,8 +265,11 @@ def main():
     launches = pointnet2_cuda.LAUNCHES[0] if runner is None else runner.kernel_launches_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
-    for i in range(3):
+    # untimed e2e warm-up: every in-flight slot gets its pinned result buffers here (cudaHostAlloc synchronises the device and
+    # takes milliseconds; inside the timed region it showed up as a 5-25 % run-to-run spread of e2e)
+    for i in range(max(3, depth + 1)):
         step_e2e(i)
+    drain()
     ms_e2e = timed_region(step_e2e, args.steps, rank_sync, drain)
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host[0])
 
