@@ -63,6 +63,9 @@ def algorithmic_bytes(name, a):
     if name == "bias_relu":
         b, c, l = a[:3]
         return 8 * b * c * l
+    if name == "attention_scale_pm":  # (rows, rc, c, ld1, ld2, ldx, ldo): r1, r2, x in, out
+        rows, rc, c = a[:3]
+        return 4 * rows * (2 * rc + 2 * c)
     if name == "three_nn_weights":  # three_nn + the (n, 3) weights
         b, n, m = a[:3]
         return b * (12 * n + 12 * m + 24 * n + 12 * n)
@@ -206,7 +209,8 @@ def measure(model, runner, dev_pool, device, world):
     for (name, ints), (tot, cnt) in agg.items():
         # plain, implicit-convolution and transposed-convolution launches are the same device code: gemm_tf32x3_kernel
         # (tiles wider than 64 columns) or gemm_tf32x3_ts_kernel (A operand through TMEM, tiles of <= 64 columns)
-        e = by_name.setdefault("gemm_tf32x3_kernel" if name in ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3") else name,
+        family = ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3", "gemm_tf32x3_grouped", "gemm_tf32x3_cm")
+        e = by_name.setdefault("gemm_tf32x3_kernel" if name in family else name,
                                {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
         e["time"] += tot / reps
         e["launches"] += cnt // reps
@@ -220,6 +224,13 @@ def measure(model, runner, dev_pool, device, world):
             ho, wo = (h_ - 1) // st_ + 1, (w_ - 1) // st_ + 1
             e["flops"] += 2.0 * b_ * ho * wo * 9 * ci_ * co_ * (cnt // reps)
             e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * 9 * ci_ * co_ + b_ * ho * wo * co_) * (cnt // reps)
+        if name == "gemm_tf32x3_cm":  # (L, K, N, pts, ldx, BN, relu)
+            e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
+            e["bytes"] += 4.0 * (ints[0] * ints[1] + 2 * ints[1] * ints[2] + ints[0] * ints[2]) * (cnt // reps)
+        if name == "gemm_tf32x3_grouped":  # (scenes, n, m, ns, c, ldf, BN, N, relu, pool, ldy): rows gathered, never materialised
+            rows_, k_, n_ = ints[0] * ints[2] * ints[3], ints[4] + 3, ints[7]
+            e["flops"] += 2.0 * rows_ * k_ * n_ * (cnt // reps)
+            e["bytes"] += 4.0 * (ints[0] * min(ints[1], ints[2] * ints[3]) * k_ + rows_ + 2 * k_ * n_ + rows_ // max(ints[9], 1) * n_) * (cnt // reps)
         if name == "deconv_nhwc_tf32x3":  # (b, h, w, cin, k, co, ldx, BN, relu, ldo): every input pixel -> a k x k x co patch
             b_, h_, w_, ci_, k_, co_ = ints[:6]
             e["flops"] += 2.0 * b_ * h_ * w_ * ci_ * k_ * k_ * co_ * (cnt // reps)
