@@ -1,6 +1,6 @@
 """Per-op timing at the backbone's shapes: the B200 kernels vs the reference's own kernels (oracle/_ref).
 CUDA-event timing, inputs resident, L2 left warm (shapes here are far below L2; these are latency numbers).
-Usage: python tools/op_bench.py [--iters 20] [--json out.json]"""
+Usage: python tests/perf/op_bench.py [--iters 20] [--json out.json]"""
 import argparse
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from epnet_b200 import pointnet2_cuda as ours  # noqa: E402
 from epnet_b200 import scenes  # noqa: E402
 

@@ -7,7 +7,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench_roofline as br  # noqa: E402
 from epnet_b200 import pointnet2_cuda as ours  # noqa: E402
 from oracle import ref_cuda  # noqa: E402
@@ -100,7 +100,7 @@ path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/op_sweep.json"
 json.dump(rows, open(path, "w"), indent=1)
 nan = float("nan")
 with open(os.path.splitext(path)[0] + ".txt", "w") as f:
-    f.write("# op-level sweep (BASELINE.json configs[4]), B=1, M=N/4; tools/op_sweep.py on one B200, CUDA events; reference kernels = "
+    f.write("# op-level sweep (BASELINE.json configs[4]), B=1, M=N/4; tests/perf/op_sweep.py on one B200, CUDA events; reference kernels = "
             "oracle/_ref (unmodified sources built for sm_100a); frac = algorithmic bytes / time / measured HBM peak\n")
     f.write(f"{'op':28s} {'shape':34s} {'ours_us':>9s} {'ref_us':>10s} {'speedup':>8s} {'alg GB/s':>9s} {'frac':>6s}\n")
     for r in rows:
