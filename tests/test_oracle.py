@@ -132,3 +132,16 @@ def test_grid_gather_matches_torch_cpu_grid_sample(align_corners):
     out.backward(go)
     got_g = oracle.grid_gather_bilinear_grad(go.numpy(), xy, 12, 20, align_corners)
     np.testing.assert_allclose(got_g, f.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fps_of_an_fps_ordered_cloud_is_the_identity_prefix():
+    """Greedy FPS is self-consistent: sampling M2 < M points from the M points an earlier FPS produced (in its output order)
+    returns 0, 1, ..., M2-1 whenever the earlier maxima were unique -- the reason every coarser level of the backbone is a
+    prefix of the finer one.  (With exact ties the reference's bit-reversal tie rule may pick a different index, so the
+    product still runs every level)"""
+    from cases import lidar
+    xyz = lidar(3, 2, 4096)
+    first = oracle.furthest_point_sampling(xyz, 1024)
+    coarse = np.stack([xyz[b][first[b]] for b in range(2)])
+    again = oracle.furthest_point_sampling(coarse, 256)
+    np.testing.assert_array_equal(again, np.broadcast_to(np.arange(256, dtype=np.int32), (2, 256)))
