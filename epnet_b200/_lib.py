@@ -40,11 +40,14 @@ SIGNATURES = {
                                   _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_gemm_tf32x3_cm": [_c_int] * 4 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p],
     "epnet_conv3x3_nhwc_tf32x3": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_conv3x3_nhwc_f16x3": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_grid_gather_nhwc_pm": [_c_int] * 5 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_deconv_nhwc_tf32x3": [_c_int] * 6 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_deconv_nhwc_f16x3": [_c_int] * 6 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_deconv_shuffle_nhwc": [_c_int] * 5 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "epnet_roipool3d": [_c_int] * 5 + [_c_void_p] * 6,
     "epnet_gemm_tf32x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_gemm_f16x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
 }
 
 

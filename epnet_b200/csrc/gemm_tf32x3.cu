@@ -22,6 +22,7 @@
 //     ReLU, 128-bit stores; with pool > 1 the max over `pool` consecutive rows (the nsample axis of a grouped
 //     tensor, F.max_pool2d in pointnet2_modules.py:59-61) is taken across lanes with redux.sync before storing.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace epnet {
 
@@ -119,6 +120,8 @@ struct GemmArgs {
     const float *g_xyz, *g_centre;
     int g_n, g_ns, g_rows_scene;
     int kcopy;             // columns of a row that are read from x (== K unless grouped)
+    int f16;               // weights are packed as FP16 planes (k-blocks of 64): wide-tile FP16-split kernel
+    float corr_scale;      // the correction accumulator is multiplied by this in the epilogue (1 for the TF32 split, 2^-11 for FP16)
 };
 
 // 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
@@ -212,6 +215,16 @@ struct RowSource {
         }
     }
 
+    // 8 consecutive floats from column k0 of this thread's first four rows (two 16-byte chunks each)
+    __device__ __forceinline__ void load4x8(const GemmArgs &a, int k0, float4 (&v)[8]) const
+    {
+        float4 lo[8], hi[8];
+        load(a, k0, lo);      // rows 4..7 of the source are not used by the caller: their loads are predicated off below
+        load(a, k0 + 4, hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = lo[i]; v[2 * i + 1] = hi[i]; }
+    }
+
     // the same chunks, copied asynchronously to base + dst_off[i] (cp.async group of the caller); rows whose base or stride
     // is not 16-byte aligned are loaded and stored synchronously instead
     __device__ __forceinline__ void copy_async(const GemmArgs &a, int k0, uint8_t *base, const uint32_t (&dst_off)[8]) const
@@ -246,13 +259,13 @@ struct RowSource {
 // Accumulator -> global memory: main + correction, bias, ReLU, then plain rows / pooled rows / the transposed convolution's
 // patch scatter.  Called by the four warps whose warp index selects the TMEM lane quarter (thread = lane = tile row).
 __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_acc, uint32_t corr_off, int warp, int lane, int row0,
-                                              int ntile, const float *bias_s)
+                                              int ntile, const float *bias_s, int c_first = 0, int c_step = 32)
 {
     const int BN = a.BN;
     const int r = warp * 32 + lane;  // TMEM lane == tile row
     const int row = row0 + r;
     const int pool = a.pool;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = c_first; c0 < BN; c0 += c_step) {
         uint32_t v[32], w[32];
         const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
         tmem_ld32(taddr, v);
@@ -262,7 +275,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
         const int n0 = ntile * BN + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(w[j])) + bias_s[c0 + j];
+            float f = __fmaf_rn(__uint_as_float(w[j]), a.corr_scale, __uint_as_float(v[j])) + bias_s[c0 + j];  // scale 1: an exact add
             if (a.relu) f = fmaxf(f, 0.f);
             v[j] = __float_as_uint(f);
         }
@@ -483,6 +496,192 @@ gemm_tf32x3_kernel(const GemmArgs a)
 
     __syncthreads();
     if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Wide tiles (BN > 64) with a two-term FP16 split instead of the TF32 split:  x = h1 + 2^-11 h2,  h1 = fp16(x),
+// h2 = fp16((x - h1) * 2^11)  (22 significand bits, like hi/lo in TF32), and likewise for W.  Three kind::f16 MMAs per 16
+// k-values (h1 g1 -> main accumulator; h1 g2 + h2 g1 -> correction accumulator, scaled back by 2^-11 in the epilogue) run at
+// twice the TF32 rate and every operand byte in shared memory carries twice as many k-values: the wide-tile kernel is bound by
+// exactly these two resources.  Inputs must stay inside fp16's range (|x| < 65504; the backbone's activations and folded
+// weights are below 10, tools/fp16_split_probe.py); values below 2^-24 lose relative but not absolute accuracy.
+// 10 warps, one CTA per SM (a 256-column tile owns all 512 TMEM columns anyway): warps 0-7 split X (a k-block is 64 k-values:
+// 256 bytes of fp32 per row in, 128 bytes per plane out) and run the epilogue, warp 8 issues the MMAs, warp 9 loads W.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kHfThreads = 320;
+constexpr int kHfProducers = 256;
+constexpr int kHfBK = 64;
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+
+__device__ __forceinline__ void split_f16(float x, __half &h1, __half &h2)
+{
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(h1)), 2048.0f));
+}
+
+__global__ void __launch_bounds__(kHfThreads, 1)
+gemm_f16x3_kernel(const GemmArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t gm_smem[];
+    __shared__ __align__(8) uint64_t full_a[kGmMaxStages], full_b[kGmMaxStages], empty[kGmMaxStages], accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float bias_s[256 + 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * kGmBM;
+    const int ntile = blockIdx.y;
+    const int BN = a.BN;
+    const uint32_t a_bytes = kGmBM * 128;        // one plane (h1 or h2) of the X tile: 128 rows x 64 halfs
+    const uint32_t b_bytes = (uint32_t)BN * 128; // one plane of the W tile
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
+    const uint32_t BNP = (uint32_t)((BN + 31) & ~31);
+    const uint32_t corr_off = BN <= 128 ? (uint32_t)BN : BNP;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2 * BNP) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(&full_a[s], kHfProducers);
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = tid; j < 256 + 32; j += kHfThreads) {
+        const int n = ntile * BN + j;
+        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp < 8) {
+        // ===================== X producers =====================
+        const int chunk = tid & 7;   // 16-byte chunk of a plane row = 8 consecutive k-values = 32 bytes of fp32 input
+        const int rbase = tid >> 3;  // 0..31; rows rbase + 32*i, i < 4
+        RowSource src;
+        src.init(a, row0 + rbase, 32);
+#pragma unroll
+        for (int i = 4; i < 8; ++i) src.rmask[i] = 0u;  // those rows belong to other threads
+        uint32_t slot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rbase + 32 * i;
+            slot[i] = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+        }
+        float4 cur[8], nxt[8];  // [2*i], [2*i+1]: the 8 floats of row i
+        src.load4x8(a, chunk * 8, cur);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < a.n_kblocks; ++kb) {
+            if (kb + 1 < a.n_kblocks) src.load4x8(a, (kb + 1) * kHfBK + chunk * 8, nxt);
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t *p1 = smem + (size_t)s * stage_bytes;
+            uint8_t *p2 = p1 + a_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x[8] = {cur[2 * i].x, cur[2 * i].y, cur[2 * i].z, cur[2 * i].w, cur[2 * i + 1].x, cur[2 * i + 1].y, cur[2 * i + 1].z, cur[2 * i + 1].w};
+                __half h1[8], h2[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_f16(x[e], h1[e], h2[e]);
+                uint4 q1, q2;
+                q1.x = (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16);
+                q1.y = (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16);
+                q1.z = (uint32_t)__half_as_ushort(h1[4]) | ((uint32_t)__half_as_ushort(h1[5]) << 16);
+                q1.w = (uint32_t)__half_as_ushort(h1[6]) | ((uint32_t)__half_as_ushort(h1[7]) << 16);
+                q2.x = (uint32_t)__half_as_ushort(h2[0]) | ((uint32_t)__half_as_ushort(h2[1]) << 16);
+                q2.y = (uint32_t)__half_as_ushort(h2[2]) | ((uint32_t)__half_as_ushort(h2[3]) << 16);
+                q2.z = (uint32_t)__half_as_ushort(h2[4]) | ((uint32_t)__half_as_ushort(h2[5]) << 16);
+                q2.w = (uint32_t)__half_as_ushort(h2[6]) | ((uint32_t)__half_as_ushort(h2[7]) << 16);
+                *reinterpret_cast<uint4 *>(p1 + slot[i]) = q1;
+                *reinterpret_cast<uint4 *>(p2 + slot[i]) = q2;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_a[s]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
+        }
+
+        // ===================== epilogue: warps w and w+4 share a TMEM lane quarter and alternate 32-column chunks =====================
+        mbar_wait(&accum_bar, 0u);
+        tc_fence_after();
+        gemm_epilogue(a, tmem_acc, corr_off, warp & 3, lane, row0, ntile, bias_s, (warp >> 2) * 32, 64);
+        tc_fence_before();
+    } else if (warp == 8) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const bool fused_b = BN <= 128;
+            // kind::f16, A and B fp16 (format 0), D fp32 (bit 4), K-major both
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_b[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t d_a1 = umma_desc_k_sw128(base), d_a2 = umma_desc_k_sw128(base + a_bytes);
+                const uint64_t d_b1 = umma_desc_k_sw128(base + 2 * a_bytes), d_b2 = umma_desc_k_sw128(base + 2 * a_bytes + b_bytes);
+#pragma unroll
+                for (int ks = 0; ks < kHfBK / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);  // 16 halfs = 32 bytes = 2 x 16 B along the swizzled row
+                    if (fused_b) {
+                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc2, (kb | ks) ? 1u : 0u);
+                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, 1u);
+                    } else {
+                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                        umma_f16(tmem_acc + corr_off, d_a1 + adv, d_b2 + adv, idesc, 1u);
+                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(&accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ===================== weight loader (one thread) =====================
+        if (lane == 0) {
+            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
+                bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full_b[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
     }
@@ -731,6 +930,7 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
 {
     a.n_kblocks = (a.K + kGmBK - 1) / kGmBK;
     if (!a.g_idx) a.kcopy = a.K;
+    if (a.corr_scale == 0.f) a.corr_scale = 1.f;
     const int n_tiles = (a.N + a.BN - 1) / a.BN;
     dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
     // the opt-in shared-memory limit is a property of the function, not of a launch: always raise it to the hardware maximum so
@@ -755,6 +955,22 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
         gemm_tf32x3_ts_kernel<<<grid, kGmThreads, smem, st>>>(a);
         EPNET_RETURN_LAUNCH_STATUS();
     }
+    if (a.f16) {  // FP16 split, k-blocks of 64, one CTA per SM
+        if (a.BN <= 64 || a.g_idx) return EPNET_ERR_BAD_ARG;
+        a.n_kblocks = (a.K + kHfBK - 1) / kHfBK;
+        a.corr_scale = 1.0f / 2048.0f;
+        const size_t sb = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
+        int st_ = (int)((200 * 1024) / sb);
+        if (st_ > kGmMaxStages) st_ = kGmMaxStages;
+        if (st_ > a.n_kblocks) st_ = a.n_kblocks;
+        if (st_ < 2 && a.n_kblocks > 1) st_ = 2;
+        if (st_ < 1) st_ = 1;
+        a.stages = st_;
+        const int e16 = raise_limit((const void *)gemm_f16x3_kernel);
+        if (e16) return e16;
+        gemm_f16x3_kernel<<<grid, kHfThreads, sb * st_ + 1024, st>>>(a);
+        EPNET_RETURN_LAUNCH_STATUS();
+    }
     const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
     int stages = (int)((100 * 1024) / stage_bytes);  // <= ~100 KB per CTA: two CTAs per SM overlap each other's epilogue
     if (stages > kGmMaxStages) stages = kGmMaxStages;
@@ -771,8 +987,8 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
 }  // namespace epnet
 
 // x (L, ldx) fp32 rows, wpack from pack_weights (N_tiles x n_kblocks x 2 x BN x 32), bias (N) or NULL -> y (L/pool, ldy).
-EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
-                                int pool, float *y, int ldy, void *stream)
+static int gemm_entry(int f16, int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
+                      int pool, float *y, int ldy, void *stream)
 {
     using namespace epnet;
     if (L < 0 || K <= 0 || N <= 0 || !x || !wpack || !y || ldx < K || ldy < N) return EPNET_ERR_BAD_ARG;
@@ -783,9 +999,20 @@ EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, co
     GemmArgs a = {};
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
     a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
-    a.relu = relu; a.pool = pool;
+    a.relu = relu; a.pool = pool; a.f16 = f16;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
     return gemm_launch(a, (cudaStream_t)stream);
+}
+EPNET_API int epnet_gemm_tf32x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
+                                int pool, float *y, int ldy, void *stream)
+{
+    return gemm_entry(0, L, K, N, x, ldx, wpack, BN, bias, relu, pool, y, ldy, stream);
+}
+// Same contract with the FP16 two-term split (wpack = FP16 planes, k-blocks of 64; BN > 64; |x|, |w| < 65504)
+EPNET_API int epnet_gemm_f16x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu,
+                               int pool, float *y, int ldy, void *stream)
+{
+    return gemm_entry(1, L, K, N, x, ldx, wpack, BN, bias, relu, pool, y, ldy, stream);
 }
 
 // First shared-MLP layer of a set-abstraction scale with the grouping fused into the operand load (QueryAndGroup + Conv2d 1x1 +
@@ -831,8 +1058,8 @@ EPNET_API int epnet_gemm_tf32x3_cm(int L, int K, int N, int pts, const float *x,
 
 // 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM on an NHWC image: x (B, H, W, Cin) with Cin a power of two
 // >= 4; wpack packs W reordered to (Cout, ky, kx, Cin) (K = 9*Cin); y (B*Ho*Wo, ldy) = NHWC output, bias/ReLU optional.
-EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
-                                        const float *bias, int relu, float *y, int ldy, void *stream)
+static int conv_entry(int f16, int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                      const float *bias, int relu, float *y, int ldy, void *stream)
 {
     using namespace epnet;
     if (b < 0 || h <= 0 || w <= 0 || cin < 4 || (cin & (cin - 1)) != 0 || cout <= 0 || (stride != 1 && stride != 2) || !x || !wpack || !y)
@@ -849,8 +1076,18 @@ EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, 
     const long long rows = (long long)b * a.Ho * a.Wo;
     if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
     a.L = (int)rows; a.K = 9 * cin; a.N = cout; a.ldx = cin; a.ldy = ldy; a.BN = BN;
-    a.relu = relu; a.pool = 1; a.x_vec_ok = 1;
+    a.relu = relu; a.pool = 1; a.x_vec_ok = 1; a.f16 = f16;
     return gemm_launch(a, (cudaStream_t)stream);
+}
+EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                                        const float *bias, int relu, float *y, int ldy, void *stream)
+{
+    return conv_entry(0, b, h, w, cin, cout, stride, x, wpack, BN, bias, relu, y, ldy, stream);
+}
+EPNET_API int epnet_conv3x3_nhwc_f16x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                                       const float *bias, int relu, float *y, int ldy, void *stream)
+{
+    return conv_entry(1, b, h, w, cin, cout, stride, x, wpack, BN, bias, relu, y, ldy, stream);
 }
 
 // Transposed convolution with kernel == stride == k (ConvTranspose2d, no overlap between patches) on an NHWC map: x rows are the
@@ -858,8 +1095,8 @@ EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, 
 // pixel's k x k x co patch straight into out, an NHWC buffer of (B, h*k, w*k) pixels ldo floats apart (out already offset to the
 // first channel of this map's slice of a concatenation); bias (k*k*co, one value per GEMM column) or NULL.  Replaces a GEMM +
 // pixel-shuffle pass.
-EPNET_API int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
-                                       const float *bias, int relu, float *out, int ldo, void *stream)
+static int deconv_entry(int f16, int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                        const float *bias, int relu, float *out, int ldo, void *stream)
 {
     using namespace epnet;
     if (b < 0 || h <= 0 || w <= 0 || cin <= 0 || k <= 0 || co <= 0 || (co % 4) != 0 || !x || !wpack || !out || ldx < cin || ldo < co)
@@ -872,7 +1109,17 @@ EPNET_API int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int 
     GemmArgs a = {};
     a.x = x; a.wpack = wpack; a.bias = bias; a.y = out;
     a.L = (int)rows; a.K = cin; a.N = (int)cols; a.ldx = ldx; a.ldy = ldo; a.BN = BN;
-    a.relu = relu; a.pool = 1; a.H = h; a.W = w; a.dk = k; a.dco = co;
+    a.relu = relu; a.pool = 1; a.H = h; a.W = w; a.dk = k; a.dco = co; a.f16 = f16;
     a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
     return gemm_launch(a, (cudaStream_t)stream);
+}
+EPNET_API int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                                       const float *bias, int relu, float *out, int ldo, void *stream)
+{
+    return deconv_entry(0, b, h, w, cin, k, co, x, ldx, wpack, BN, bias, relu, out, ldo, stream);
+}
+EPNET_API int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                                      const float *bias, int relu, float *out, int ldo, void *stream)
+{
+    return deconv_entry(1, b, h, w, cin, k, co, x, ldx, wpack, BN, bias, relu, out, ldo, stream);
 }

@@ -1,5 +1,6 @@
 """Host side of the tcgen05 3xTF32 GEMM (csrc/gemm_tf32x3.cu): weight packing and the launch wrapper."""
 import contextlib
+import os as _os
 
 import torch
 
@@ -13,6 +14,11 @@ BK = 32
 # and the GPU is full anyway.  Measured on the backbone: latency tiles 3.51 -> 3.25 ms per single batch, but -1.3 % scenes/s
 # with six batches in flight.
 _TILE_POLICY = "latency"
+
+# Wide tiles (BN > 64) on the FP16 two-term split (csrc/gemm_tf32x3.cu, gemm_f16x3_kernel) instead of the TF32 split: same 22
+# significand bits, twice the MMA rate, half the operand bytes.  Needs |x|, |w| < 65504 (fp16 range).
+F16_WIDE = _os.environ.get("EPNET_F16_WIDE", "1") != "0"
+BK16 = 64
 
 
 @contextlib.contextmanager
@@ -79,6 +85,29 @@ class PackedLinear:
             self._packs[bn] = torch.gather(planes, 4, idx).contiguous()
         return self._packs[bn]
 
+    def _pack16(self, bn):
+        """FP16 planes: h1 = fp16(w), h2 = fp16((w - h1) * 2^11); k-blocks of 64 halfs = one 128-byte swizzle row"""
+        key = ("f16", bn)
+        if key not in self._packs:
+            w, dev = self._w, self._w.device
+            n_tiles = (self.N + bn - 1) // bn
+            nkb = (self.K + BK16 - 1) // BK16
+            wp = torch.zeros(n_tiles * bn, nkb * BK16, device=dev)
+            wp[:self.N, :self.K] = w
+            h1 = wp.half()
+            h2 = ((wp - h1.float()) * 2048.0).half()
+            planes = torch.stack([h1, h2]).view(2, n_tiles, bn, nkb, 8, 8)       # k = kb*64 + c*8 + e
+            planes = planes.permute(1, 3, 0, 2, 4, 5).contiguous()               # (tile, kb, plane, row, c, e)
+            r = torch.arange(bn, device=dev) % 8
+            c = torch.arange(8, device=dev)
+            idx = (c[None, :] ^ r[:, None])[None, None, None, :, :, None].expand(n_tiles, nkb, 2, bn, 8, 8)
+            self._packs[key] = torch.gather(planes, 4, idx).contiguous()
+        return self._packs[key]
+
+    def wide_f16(self, bn):
+        """True when a launch with this column tile should take the FP16-split kernel"""
+        return F16_WIDE and bn > 64
+
     def for_rows(self, rows):
         """(BN, packed weights) for a launch over `rows` rows: packed on first use per tile width, then cached (warm the shapes
         before capturing a CUDA graph)."""
@@ -108,7 +137,10 @@ class PackedLinear:
         assert out.stride(-1) == 1
         ldy = out.stride(0)
         bn, wpack = self.for_rows(L)
-        pc._call("gemm_tf32x3", LIB.epnet_gemm_tf32x3, x2, L, self.K, self.N, x2.data_ptr(), ldx, wpack.data_ptr(), bn,
+        fn = LIB.epnet_gemm_tf32x3
+        if self.wide_f16(bn):
+            fn, wpack = LIB.epnet_gemm_f16x3, self._pack16(bn)
+        pc._call("gemm_tf32x3", fn, x2, L, self.K, self.N, x2.data_ptr(), ldx, wpack.data_ptr(), bn,
                  None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), pool, out.data_ptr(), ldy)
         return out
 
@@ -155,7 +187,10 @@ class PackedDeconv:
         assert out.stride(-3) == w * self.k * ldo and out.stride(0) == h * self.k * w * self.k * ldo
         lin = self.lin
         bn, wpack = lin.for_rows(B * h * w)
-        pc._call("deconv_nhwc_tf32x3", LIB.epnet_deconv_nhwc_tf32x3, x, B, h, w, self.cin, self.k, self.cout, x.data_ptr(), ldx,
+        fn = LIB.epnet_deconv_nhwc_tf32x3
+        if lin.wide_f16(bn):
+            fn, wpack = LIB.epnet_deconv_nhwc_f16x3, lin._pack16(bn)
+        pc._call("deconv_nhwc_tf32x3", fn, x, B, h, w, self.cin, self.k, self.cout, x.data_ptr(), ldx,
                  wpack.data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(), ldo)
         return out
 
@@ -185,7 +220,10 @@ class PackedConv3x3:
         assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
         lin = self.lin
         bn, wpack = lin.for_rows(B * Ho * Wo)
-        pc._call("conv3x3_nhwc_tf32x3", LIB.epnet_conv3x3_nhwc_tf32x3, x, B, H, W, self.cin_p, self.cout, self.stride, x.data_ptr(),
+        fn = LIB.epnet_conv3x3_nhwc_tf32x3
+        if lin.wide_f16(bn):
+            fn, wpack = LIB.epnet_conv3x3_nhwc_f16x3, lin._pack16(bn)
+        pc._call("conv3x3_nhwc_tf32x3", fn, x, B, H, W, self.cin_p, self.cout, self.stride, x.data_ptr(),
                  wpack.data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), out.data_ptr(),
                  out.stride(-2))
         return out

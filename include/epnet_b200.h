@@ -143,6 +143,16 @@ int epnet_three_nn_weights(int b, int n, int m, const float *unknown, const floa
 int epnet_grid_gather_pm(int b, int c, int h, int w, int n, const float *fmap, const float *xy, int align_corners, float *out, int ldo,
                          void *stream);
 
+/* The three wide-tile entry points (BN > 64) with the operands split into two FP16 terms instead of TF32 hi/lo:
+ * x = h1 + 2^-11 h2 carries the same 22 significand bits, the MMAs run at twice the TF32 rate and every shared-memory byte holds
+ * twice as many k-values.  wpack = FP16 planes in k-blocks of 64 (epnet_b200/gemm.py).  |x| and |w| must stay below 65504. */
+int epnet_gemm_f16x3(int L, int K, int N, const float *x, int ldx, const float *wpack, int BN, const float *bias, int relu, int pool,
+                     float *y, int ldy, void *stream);
+int epnet_conv3x3_nhwc_f16x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                             const float *bias, int relu, float *y, int ldy, void *stream);
+int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
+                            const float *bias, int relu, float *out, int ldo, void *stream);
+
 /* First shared-MLP layer of a set-abstraction scale with QueryAndGroup fused into the operand load (pointnet2_utils.py:241-264 +
  * pointnet2_modules.py:47-52): GEMM row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], 0..c) | xyz[scene, idx] -
  * new_xyz[scene, p]] is gathered straight into the tensor-core operand, the grouped tensor is never written.  feats point-major
