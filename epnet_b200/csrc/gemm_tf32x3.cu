@@ -941,22 +941,8 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
         if (e != cudaSuccess) return (int)e;
         return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
     };
-    if (a.BN <= 64) {  // narrow tile: X through TMEM, shared memory holds only a ring of weight k-blocks
-        int stages = a.n_kblocks < kTsMaxBStages ? a.n_kblocks : kTsMaxBStages;
-        a.stages = stages < 1 ? 1 : stages;
-        a.depth = a.n_kblocks < 3 ? a.n_kblocks : 3;  // 48 KB of X + <= 48 KB of W per CTA: two CTAs per SM
-        const size_t smem = (size_t)4 * a.depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
-        const int e = raise_limit((const void *)gemm_tf32x3_ts_kernel);
-        if (e) return e;
-        // persistent over m-tiles: two CTAs per SM in total, each walking its share of the tiles of one n-tile, so TMEM
-        // allocation, barrier set-up and CTA launch/exit are paid once per CTA instead of once per 128 rows
-        const int per_ntile = (2 * kSmCount + n_tiles - 1) / n_tiles;
-        if ((int)grid.x > per_ntile) grid.x = per_ntile;
-        gemm_tf32x3_ts_kernel<<<grid, kGmThreads, smem, st>>>(a);
-        EPNET_RETURN_LAUNCH_STATUS();
-    }
     if (a.f16) {  // FP16 split, k-blocks of 64, one CTA per SM
-        if (a.BN <= 64 || a.g_idx) return EPNET_ERR_BAD_ARG;
+        if (a.g_idx) return EPNET_ERR_BAD_ARG;
         a.n_kblocks = (a.K + kHfBK - 1) / kHfBK;
         a.corr_scale = 1.0f / 2048.0f;
         const size_t sb = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
@@ -969,6 +955,20 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
         const int e16 = raise_limit((const void *)gemm_f16x3_kernel);
         if (e16) return e16;
         gemm_f16x3_kernel<<<grid, kHfThreads, sb * st_ + 1024, st>>>(a);
+        EPNET_RETURN_LAUNCH_STATUS();
+    }
+    if (a.BN <= 64) {  // narrow tile: X through TMEM, shared memory holds only a ring of weight k-blocks
+        int stages = a.n_kblocks < kTsMaxBStages ? a.n_kblocks : kTsMaxBStages;
+        a.stages = stages < 1 ? 1 : stages;
+        a.depth = a.n_kblocks < 3 ? a.n_kblocks : 3;  // 48 KB of X + <= 48 KB of W per CTA: two CTAs per SM
+        const size_t smem = (size_t)4 * a.depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
+        const int e = raise_limit((const void *)gemm_tf32x3_ts_kernel);
+        if (e) return e;
+        // persistent over m-tiles: two CTAs per SM in total, each walking its share of the tiles of one n-tile, so TMEM
+        // allocation, barrier set-up and CTA launch/exit are paid once per CTA instead of once per 128 rows
+        const int per_ntile = (2 * kSmCount + n_tiles - 1) / n_tiles;
+        if ((int)grid.x > per_ntile) grid.x = per_ntile;
+        gemm_tf32x3_ts_kernel<<<grid, kGmThreads, smem, st>>>(a);
         EPNET_RETURN_LAUNCH_STATUS();
     }
     const size_t stage_bytes = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
