@@ -942,7 +942,7 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
         return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
     };
     if (a.f16) {  // FP16 split, k-blocks of 64, one CTA per SM
-        if (a.g_idx) return EPNET_ERR_BAD_ARG;
+        if (a.g_idx || a.BN <= 64) return EPNET_ERR_BAD_ARG;  // narrow tiles stay on the TF32 A-from-TMEM kernel
         a.n_kblocks = (a.K + kHfBK - 1) / kHfBK;
         a.corr_scale = 1.0f / 2048.0f;
         const size_t sb = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
