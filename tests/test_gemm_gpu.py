@@ -159,3 +159,26 @@ def test_grouped_first_layer_equals_group_then_gemm(B, n, m, ns, c, N):
         assert lin.for_rows(B * m * ns)[0] > 64  # wide tiles take the two-step path
     else:
         assert torch.equal(fused, two_step)
+
+
+@pytest.mark.parametrize("f16_wide", [True, False])
+def test_wide_tiles_both_splits(monkeypatch, f16_wide):
+    """tiles wider than 64 columns run the FP16 two-term split by default and the TF32 split with gemm.F16_WIDE off: both are
+    fp32-grade, and they are different kernels (results differ in the last bits)"""
+    from epnet_b200 import gemm
+    monkeypatch.setattr(gemm, "F16_WIDE", f16_wide)
+    g = torch.Generator(device="cpu").manual_seed(17)
+    x = (torch.randn(3000, 700, generator=g) * 3).cuda()
+    lin = gemm.PackedLinear((torch.randn(300, 700, generator=g) / 26).cuda(), torch.randn(300, generator=g).cuda())
+    conv = gemm.PackedConv3x3((torch.randn(256, 128, 3, 3, generator=g) / 34).cuda(), torch.randn(256, generator=g).cuda())
+    xi = torch.randn(1, 24, 40, 128, generator=g).cuda()
+    with gemm.tile_policy("throughput"):  # widest tiles whatever the row count
+        assert lin.for_rows(3000)[0] > 64 and lin.wide_f16(lin.for_rows(3000)[0]) == f16_wide
+        y = lin(x, relu=False)
+        yc = conv(xi, relu=True)
+    torch.cuda.synchronize()
+    want = _ref(x, lin._w, lin.bias, False, 1)
+    assert (y.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
+    wantc = torch.nn.functional.conv2d(xi.permute(0, 3, 1, 2).double(), conv.lin._w.view(256, 3, 3, 128).permute(0, 3, 1, 2).double(),
+                                       conv.lin.bias.double(), padding=1).clamp_min(0).permute(0, 2, 3, 1)
+    assert (yc.double() - wantc).abs().max().item() <= 1e-5 * wantc.abs().max().item()
