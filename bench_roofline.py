@@ -217,6 +217,7 @@ def measure(model, runner, dev_pool, device, world):
         e["bytes"] += algorithmic_bytes(name, ints) * (cnt // reps)
         if name in ("ball_query", "three_nn", "three_nn_weights"):  # exhaustive searches: (b, n, m, ...) -> b*n*m distance tests
             e["tests"] = e.get("tests", 0.0) + float(ints[0]) * ints[1] * ints[2] * (cnt // reps)
+        before = e["flops"]
         if name == "gemm_tf32x3":
             e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
         if name == "conv3x3_nhwc_tf32x3":  # (b, h, w, cin, cout, stride, BN, relu, ldy)
@@ -235,6 +236,13 @@ def measure(model, runner, dev_pool, device, world):
             b_, h_, w_, ci_, k_, co_ = ints[:6]
             e["flops"] += 2.0 * b_ * h_ * w_ * ci_ * k_ * k_ * co_ * (cnt // reps)
             e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * ci_ * k_ * k_ * co_ + b_ * h_ * w_ * k_ * k_ * co_) * (cnt // reps)
+        # tiles wider than 64 columns run the FP16 two-term split (kind::f16 MMAs: the bf16 peak), the others the TF32 split (half
+        # of it); either way three MMAs per fp32-equivalent product
+        bn_at = {"gemm_tf32x3": 4, "conv3x3_nhwc_tf32x3": 6, "deconv_nhwc_tf32x3": 7}.get(name)
+        if e["flops"] > before:
+            from epnet_b200 import gemm as _g
+            f16 = bn_at is not None and _g.F16_WIDE and ints[bn_at] > 64
+            e["ideal_tf32_flops"] = e.get("ideal_tf32_flops", 0.0) + 3.0 * (e["flops"] - before) * (0.5 if f16 else 1.0)
     bf16_peak = 1383.2
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -246,8 +254,11 @@ def measure(model, runner, dev_pool, device, world):
         row = {"kernel": name, "launches_per_step": e["launches"], "us_per_step": round(e["time"] * 1e6, 1),
                "share_of_device_time": round(e["time"] / device_s, 4)}
         if e["flops"] > 0:  # tcgen05 3xTF32: the tensor pipe executes 3 TF32 MMAs per fp32-equivalent product
-            row.update({"bound": "tensor", "achieved": round(3 * e["flops"] / e["time"] / 1e12, 1), "peak": round(bf16_peak / 2, 1),
-                        "unit": "TFLOP/s", "frac": round(3 * e["flops"] / e["time"] / 1e12 / (bf16_peak / 2), 4),
+            # achieved = tensor-core work in TF32-MMA units: 3 MMAs per product, an FP16-split MMA counting half (it runs at twice
+            # the rate), against the dense TF32 peak -- i.e. frac = the time the MMAs alone would need at peak / the time taken
+            work = e.get("ideal_tf32_flops", 3 * e["flops"])
+            row.update({"bound": "tensor", "achieved": round(work / e["time"] / 1e12, 1), "peak": round(bf16_peak / 2, 1),
+                        "unit": "TFLOP/s", "frac": round(work / e["time"] / 1e12 / (bf16_peak / 2), 4),
                         "fp32_equiv_tflops": round(e["flops"] / e["time"] / 1e12, 1)})
         else:
             row.update({"bound": "hbm", "achieved": round(e["bytes"] / e["time"] / 1e9, 1), "peak": peak, "unit": "GB/s",
