@@ -253,6 +253,9 @@ def measure(model, runner, dev_pool, device, world):
     for name, e in sorted(by_name.items(), key=lambda kv: -kv[1]["time"]):
         row = {"kernel": name, "launches_per_step": e["launches"], "us_per_step": round(e["time"] * 1e6, 1),
                "share_of_device_time": round(e["time"] / device_s, 4)}
+        if name == "gemm_tf32x3_kernel":
+            row["device_kernels"] = ["gemm_tf32x3_ts_kernel (tiles <= 64 columns)", "gemm_f16x3_kernel (wider tiles)",
+                                     "gemm_tf32x3_kernel (wider tiles with EPNET_F16_WIDE=0)"]
         if e["flops"] > 0:  # tcgen05 3xTF32: the tensor pipe executes 3 TF32 MMAs per fp32-equivalent product
             # achieved = tensor-core work in TF32-MMA units: 3 MMAs per product, an FP16-split MMA counting half (it runs at twice
             # the rate), against the dense TF32 peak -- i.e. frac = the time the MMAs alone would need at peak / the time taken
