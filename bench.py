@@ -255,9 +255,15 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # nvidia-smi needs a few hundred ms to start reporting: it runs through warm-up and the timed region
+    last = None
     for i in range(max(args.warmup, 3)):
-        step_resident(i)
+        last = step_resident(i)
     torch.cuda.synchronize()
+    if args.mode == "infer" and last is not None:
+        # untimed sanity check of the measured configuration: the wide GEMM tiles split their operands into FP16 terms, which
+        # needs |activation| < 65504; an overflow would surface here as inf/nan (EPNET_F16_WIDE=0 selects the TF32 split)
+        if not bool(torch.isfinite(last[1]).all()):
+            raise RuntimeError("non-finite backbone output in the benchmarked configuration")
     pointnet2_cuda.LAUNCHES[0] = 0
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` sees exactly the timed steps (no-op otherwise)
     ms = timed_region(step_resident, args.steps, rank_sync, drain)

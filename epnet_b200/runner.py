@@ -106,7 +106,9 @@ class _FusionPM:
 
 class BackboneRunner:
     def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency"):
-        """layout "pm": point-major activations + tcgen05 3xTF32 GEMMs (default); "cm": channel-major + cuBLAS.
+        """layout "pm": point-major activations + tcgen05 fp32-grade GEMMs (default); "cm": channel-major + cuBLAS.
+        The wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE): activations and folded weights must stay below
+        65504 in magnitude (they are below 10 for the published configuration); set EPNET_F16_WIDE=0 for the TF32 split.
         tiles: gemm.tile_policy for every GEMM launch of this runner ("latency" for one batch at a time)."""
         assert layout in ("pm", "cm")
         self.layout = layout
