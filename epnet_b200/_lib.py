@@ -46,6 +46,11 @@ SIGNATURES = {
     "epnet_deconv_nhwc_f16x3": [_c_int] * 6 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_deconv_shuffle_nhwc": [_c_int] * 5 + [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
     "epnet_roipool3d": [_c_int] * 5 + [_c_void_p] * 6,
+    "epnet_boxes_overlap_bev": [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p],
+    "epnet_boxes_iou_bev": [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p],
+    "epnet_nms_workspace_bytes": [_c_int, _c_int, ctypes.POINTER(ctypes.c_ulonglong)],
+    "epnet_nms_rotated": [_c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int] + [_c_void_p] * 4,
+    "epnet_nms_normal": [_c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int] + [_c_void_p] * 4,
     "epnet_gemm_tf32x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_gemm_f16x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
 }

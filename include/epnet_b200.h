@@ -200,6 +200,35 @@ int epnet_deconv_nhwc_tf32x3(int b, int h, int w, int cin, int k, int co, const 
 int epnet_roipool3d(int b, int n, int m, int c, int sampled, const float *xyz, const float *boxes3d, const float *pts_feature,
                     float *pooled_features, int *pooled_empty_flag, void *stream);
 
+/* ---- next row of the scope table: rotated BEV overlap / IoU and NMS -------------------------- */
+
+/* replaces boxesoverlapLauncher (/root/reference/lib/utils/iou3d/src/iou3d_kernel.cu:352-361, called from iou3d.cpp:34-52).
+ * boxes_a (num_a,5), boxes_b (num_b,5) as [x1, y1, x2, y2, ry] -> ans_overlap (num_a,num_b): area of the intersection of
+ * the two rotated rectangles.  Same floating-point expression as the reference (bit-identical values). */
+int epnet_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_overlap, void *stream);
+
+/* replaces boxesioubevLauncher (iou3d_kernel.cu:363-369, iou3d.cpp:54-72): ans_iou (num_a,num_b) = overlap / max(sa + sb - overlap, 1e-8). */
+int epnet_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_iou, void *stream);
+
+/* bytes of scratch the two NMS entry points need for `s` problems of up to `n` boxes: s * n * ceil(n/64) 64-bit words
+ * (the reference cudaMallocs and frees this per call: iou3d.cpp:86-88,98). */
+int epnet_nms_workspace_bytes(int s, int n, unsigned long long *bytes);
+
+/* replaces nmsLauncher (iou3d_kernel.cu:372-377) PLUS the host half of nms_gpu (iou3d.cpp:74-121: D2H copy of the mask and
+ * the serial greedy loop).  `s` independent problems in one launch: boxes (s,n,5), each problem sorted by descending score by
+ * the caller (iou3d_utils.py:62-64); counts (s) = boxes actually present per problem, or NULL for n everywhere;
+ * a box is suppressed by an earlier kept box when their rotated BEV IoU > thresh.  keep (s,n) int64: indices of the kept
+ * boxes in ascending order (first num_out[p] entries valid, the rest untouched); num_out (s).  max_out > 0 stops each problem
+ * after that many kept boxes (what the proposal layer truncates to, lib/rpn/proposal_layer.py:111); <= 0 = no limit.
+ * workspace: epnet_nms_workspace_bytes(s, n) bytes, 8-byte aligned, contents irrelevant.  Keep-sets are identical to the reference's. */
+int epnet_nms_rotated(int s, int n, const float *boxes, const int *counts, float thresh, int max_out, void *workspace, long long *keep,
+                      int *num_out, void *stream);
+
+/* replaces nmsNormalLauncher (iou3d_kernel.cu:380-385) plus the host half of nms_normal_gpu (iou3d.cpp:124-170): the same
+ * with the axis-aligned IoU of the [x1,y1,x2,y2] extents (the angle is ignored). */
+int epnet_nms_normal(int s, int n, const float *boxes, const int *counts, float thresh, int max_out, void *workspace, long long *keep,
+                     int *num_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,9 @@ _interp_grad = _sig("oracle_three_interpolate_grad", _i, _i, _i, _i, _F, _I, _F,
 _grid = _sig("oracle_grid_gather_bilinear", _i, _i, _i, _i, _i, _F, _F, _i, _F)
 _grid_grad = _sig("oracle_grid_gather_bilinear_grad", _i, _i, _i, _i, _i, _F, _F, _i, _F)
 _roi = _sig("oracle_roipool3d", _i, _i, _i, _i, _i, _F, _F, _F, _F, _I)
+_pair = _sig("oracle_boxes_pairwise_bev", _i, _i, _F, _i, _F, _F)
+_lib.oracle_nms_bev.argtypes = [_i, _i, _F, _f, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+_lib.oracle_nms_bev.restype = _i
 _lib.oracle_fps_block_size.argtypes = [_i]
 _lib.oracle_fps_block_size.restype = _i
 
@@ -181,6 +184,34 @@ def roipool3d(pts, pts_feature, boxes3d, sampled=512):
     flag = np.zeros((B, M), dtype=np.int32)
     _roi(B, N, M, C, sampled, pts, boxes3d, pts_feature, out, flag)
     return out, flag
+
+
+def boxes_overlap_bev(boxes_a, boxes_b):
+    """(M,5), (N,5) [x1,y1,x2,y2,ry] -> (M,N) intersection areas (iou3d_kernel.cu box_overlap)."""
+    return _pairwise(0, boxes_a, boxes_b)
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    return _pairwise(1, boxes_a, boxes_b)
+
+
+def boxes_iou_normal(boxes_a, boxes_b):
+    return _pairwise(2, boxes_a, boxes_b)
+
+
+def _pairwise(mode, boxes_a, boxes_b):
+    boxes_a, boxes_b = _f32(boxes_a).reshape(-1, 5), _f32(boxes_b).reshape(-1, 5)
+    out = np.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=np.float32)
+    _pair(mode, boxes_a.shape[0], boxes_a, boxes_b.shape[0], boxes_b, out)
+    return out
+
+
+def nms_bev(boxes, thresh, rotated=True):
+    """boxes (N,5) sorted by descending score -> kept indices (int64), greedy as iou3d.cpp:100-113."""
+    boxes = _f32(boxes).reshape(-1, 5)
+    keep = np.zeros(max(boxes.shape[0], 1), dtype=np.int64)
+    k = _lib.oracle_nms_bev(int(bool(rotated)), boxes.shape[0], boxes, float(thresh), keep)
+    return keep[:k].copy()
 
 
 def fps_tie_rule_bruteforce(xyz, npoint):

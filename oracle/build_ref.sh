@@ -21,6 +21,8 @@ for f in sampling_gpu ball_query_gpu group_points_gpu interpolate_gpu; do
 done
 ROI=${EPNET_REFERENCE_ROI:-/root/reference/lib/utils/roipool3d/src}
 $NVCC $FLAGS -c "$ROI/roipool3d_kernel.cu" -o "$OUT/roipool3d_kernel.o"   # next-row oracle: the reference's RoI pooling kernels, unmodified
+IOU=${EPNET_REFERENCE_IOU:-/root/reference/lib/utils/iou3d/src}
+$NVCC $FLAGS -c "$IOU/iou3d_kernel.cu" -o "$OUT/iou3d_kernel.o"   # next-row oracle: the reference's rotated IoU / NMS kernels, unmodified
 $NVCC $FLAGS -c "$HERE/ref_shim.cu" -o "$OUT/ref_shim.o"
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libpointnet2_ref.so" "$OUT"/*.o -lcudart
 rm -f "$OUT"/*.o

@@ -344,3 +344,163 @@ ORACLE_API void oracle_roipool3d(int b, int n, int m, int c, int sampled, const 
         }
     free(sel);
 }
+
+/* ---- next row: rotated BEV overlap / IoU / NMS ---------------------------------------------------
+ * /root/reference/lib/utils/iou3d/src/iou3d_kernel.cu: cross (:34-40), check_rect_cross (:42-48), check_in_box2d (:50-65),
+ * intersection (:67-97), rotate_around_center (:99-103), point_cmp (:105-107), box_overlap (:109-226), iou_bev (:228-235),
+ * iou_normal (:296-304), the mask kernels (:262-293, :307-338) and the host greedy loop of iou3d.cpp:100-113 / :150-163.
+ * Arithmetic as nvcc -O2 compiles the reference, read off the SASS (cuobjdump) of the unmodified file -- NOT the PTX: the
+ * PTX leaves most `a*b - c*d` as mul, mul, sub without rounding modifiers and ptxas then contracts them.  In all four
+ * kernels: a*b - c*d = fma(a, b, -(c*d)) (second product rounded, first fused) for the cross products s1/s3/s4, the
+ * intersection numerators, c0/c1/D, the rotated y and the area terms; s2/s5 are the exception (shared products, see below);
+ * rotated x = fma(cos, dx, sin*dy); sa + sb = fma(wa, ha, wb*hb) in iou_bev and fma(wb, hb, wa*ha) in iou_normal;
+ * fabs(area) / 2.0 is a float multiply by 0.5.  cosf / sinf / atan2f come from the C library here and
+ * from libdevice on the GPU and may differ in the last bit, so overlaps agree to ~1e-6 relative rather than bit for bit and
+ * a keep-set can differ only where an IoU lies within that distance of the threshold; the bit-exact pin of the product is
+ * the reference's own kernels in oracle/_ref (tests/test_iou3d.py). */
+typedef struct { float x, y; } o_pt;
+
+/* a*b - c*d as the reference's binary evaluates it: the second product rounded, the first fused into the subtraction */
+static float o_pmp(float a, float b, float c, float d)
+{
+    const float cd = c * d;
+    return fmaf(a, b, -cd);
+}
+
+static float o_cross3(o_pt p1, o_pt p2, o_pt p0)
+{
+    return o_pmp(p1.x - p0.x, p2.y - p0.y, p2.x - p0.x, p1.y - p0.y);
+}
+
+static int o_intersection(o_pt p1, o_pt p0, o_pt q1, o_pt q0, o_pt *ans)
+{
+    if (!(fminf(p0.x, p1.x) <= fmaxf(q0.x, q1.x) && fminf(q0.x, q1.x) <= fmaxf(p0.x, p1.x) && fminf(p0.y, p1.y) <= fmaxf(q0.y, q1.y) &&
+          fminf(q0.y, q1.y) <= fmaxf(p0.y, p1.y)))
+        return 0;
+    const float s1 = o_cross3(q0, p1, p0), s3 = o_cross3(p0, q1, q0), s4 = o_cross3(q1, p1, q0);
+    /* the two products of s2 = cross(p1, q1, p0) are shared with s5 = cross(q1, p1, p0) = -s2, which lives behind a branch:
+     * both stay rounded multiplies */
+    const float m73 = (p1.x - p0.x) * (q1.y - p0.y), m74 = (q1.x - p0.x) * (p1.y - p0.y);
+    const float s2 = m73 - m74;
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    const float s5 = m74 - m73;
+    if (fabsf(s5 - s1) > 1e-8f) {
+        ans->x = o_pmp(s5, q0.x, s1, q1.x) / (s5 - s1);
+        ans->y = o_pmp(s5, q0.y, s1, q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = o_pmp(p0.x, p1.y, p1.x, p0.y);
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = o_pmp(q0.x, q1.y, q1.x, q0.y);
+        const float D = o_pmp(a0, b1, a1, b0);
+        ans->x = o_pmp(b0, c1, b1, c0) / D;
+        ans->y = o_pmp(a1, c0, a0, c1) / D;
+    }
+    return 1;
+}
+
+static o_pt o_rotate(o_pt c, float cosa, float sina, o_pt p)
+{
+    const float dx = p.x - c.x, dy = p.y - c.y;
+    const float t = sina * dy;
+    o_pt r;
+    r.x = c.x + fmaf(cosa, dx, t);
+    r.y = c.y + o_pmp(cosa, dy, sina, dx);
+    return r;
+}
+
+static int o_in_box2d(const float *box, o_pt p)
+{
+    o_pt c;
+    c.x = (box[0] + box[2]) * 0.5f;
+    c.y = (box[1] + box[3]) * 0.5f;
+    const o_pt r = o_rotate(c, cosf(-box[4]), sinf(-box[4]), p);
+    return r.x > box[0] + -1e-5f && r.x < box[2] + 1e-5f && r.y > box[1] + -1e-5f && r.y < box[3] + 1e-5f;
+}
+
+static float o_box_overlap(const float *a, const float *b)
+{
+    o_pt ca, cb, pa[5], pb[5], pts[32], centre = {0.0f, 0.0f};
+    ca.x = (a[0] + a[2]) * 0.5f; ca.y = (a[1] + a[3]) * 0.5f;
+    cb.x = (b[0] + b[2]) * 0.5f; cb.y = (b[1] + b[3]) * 0.5f;
+    const float xs_a[4] = {a[0], a[2], a[2], a[0]}, ys_a[4] = {a[1], a[1], a[3], a[3]};
+    const float xs_b[4] = {b[0], b[2], b[2], b[0]}, ys_b[4] = {b[1], b[1], b[3], b[3]};
+    const float cos_a = cosf(a[4]), sin_a = sinf(a[4]), cos_b = cosf(b[4]), sin_b = sinf(b[4]);
+    for (int k = 0; k < 4; ++k) {
+        o_pt p = {xs_a[k], ys_a[k]}, q = {xs_b[k], ys_b[k]};
+        pa[k] = o_rotate(ca, cos_a, sin_a, p);
+        pb[k] = o_rotate(cb, cos_b, sin_b, q);
+    }
+    pa[4] = pa[0];
+    pb[4] = pb[0];
+    int cnt = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (o_intersection(pa[i + 1], pa[i], pb[j + 1], pb[j], &pts[cnt])) {
+                centre.x += pts[cnt].x; centre.y += pts[cnt].y;
+                ++cnt;
+            }
+    for (int k = 0; k < 4; ++k) {
+        if (o_in_box2d(a, pb[k])) { centre.x += pb[k].x; centre.y += pb[k].y; pts[cnt++] = pb[k]; }
+        if (o_in_box2d(b, pa[k])) { centre.x += pa[k].x; centre.y += pa[k].y; pts[cnt++] = pa[k]; }
+    }
+    centre.x /= (float)cnt;
+    centre.y /= (float)cnt;
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(pts[i].y - centre.y, pts[i].x - centre.x) > atan2f(pts[i + 1].y - centre.y, pts[i + 1].x - centre.x)) {
+                const o_pt t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+            }
+    float area = 0.0f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ux = pts[k].x - pts[0].x, uy = pts[k].y - pts[0].y, vx = pts[k + 1].x - pts[0].x, vy = pts[k + 1].y - pts[0].y;
+        area += o_pmp(ux, vy, uy, vx);
+    }
+    return fabsf(area) * 0.5f;
+}
+
+static float o_iou_bev(const float *a, const float *b)
+{
+    const float sb = (b[2] - b[0]) * (b[3] - b[1]);
+    const float sum = fmaf(a[2] - a[0], a[3] - a[1], sb);
+    const float ov = o_box_overlap(a, b);
+    return ov / fmaxf(sum - ov, 1e-8f);
+}
+
+static float o_iou_normal(const float *a, const float *b)
+{
+    const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]), top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+    const float w = fmaxf(right - left, 0.0f), h = fmaxf(bottom - top, 0.0f), inter = w * h;
+    const float sa = (a[2] - a[0]) * (a[3] - a[1]);
+    const float sum = fmaf(b[2] - b[0], b[3] - b[1], sa);
+    return inter / fmaxf(sum - inter, 1e-8f);
+}
+
+/* mode 0: overlap area, 1: rotated IoU, 2: axis-aligned IoU; out (num_a, num_b) */
+ORACLE_API void oracle_boxes_pairwise_bev(int mode, int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < num_a; ++i)
+        for (int j = 0; j < num_b; ++j) {
+            const float *a = boxes_a + (size_t)i * 5, *b = boxes_b + (size_t)j * 5;
+            out[(size_t)i * num_b + j] = mode == 0 ? o_box_overlap(a, b) : mode == 1 ? o_iou_bev(a, b) : o_iou_normal(a, b);
+        }
+}
+
+/* boxes (n,5) already sorted by descending score; keep (n) receives the kept indices; returns how many.  The suppression
+ * bits are the reference's (row i against every later box j, `iou > thresh`), the scan is iou3d.cpp:100-113. */
+ORACLE_API int oracle_nms_bev(int rotated, int n, const float *boxes, float thresh, long long *keep)
+{
+    unsigned char *removed = (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+        if (removed[i]) continue;
+        keep[kept++] = i;
+#pragma omp parallel for schedule(static)
+        for (int j = i + 1; j < n; ++j) {
+            if (removed[j]) continue;
+            const float v = rotated ? o_iou_bev(boxes + (size_t)i * 5, boxes + (size_t)j * 5) : o_iou_normal(boxes + (size_t)i * 5, boxes + (size_t)j * 5);
+            if (v > thresh) removed[j] = 1;
+        }
+    }
+    free(removed);
+    return kept;
+}

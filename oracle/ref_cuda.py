@@ -37,6 +37,10 @@ def _load():
             "ref_three_interpolate": [_c_int] * 4 + [_c_void_p] * 5,
             "ref_three_interpolate_grad": [_c_int] * 4 + [_c_void_p] * 5,
             "ref_roipool3d": [_c_int] * 5 + [_c_void_p] * 5,
+            "ref_boxes_overlap_bev": [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p],
+            "ref_boxes_iou_bev": [_c_int, _c_void_p, _c_int, _c_void_p, _c_void_p],
+            "ref_nms_mask": [_c_void_p, _c_void_p, _c_int, _c_float],
+            "ref_nms_normal_mask": [_c_void_p, _c_void_p, _c_int, _c_float],
         }
         for name, argtypes in sigs.items():
             fn = getattr(lib, name)
@@ -114,3 +118,34 @@ def roipool3d(pts, boxes3d, pts_feature, sampled=512):
     _load().ref_roipool3d(B, N, M, C, sampled, _p(pts), _p(boxes3d), _p(pts_feature), _p(out), _p(flag))
     torch.cuda.synchronize()
     return out, flag
+
+
+def boxes_pairwise_bev(boxes_a, boxes_b, iou):
+    """The reference's boxesoverlapLauncher (iou=False) / boxesioubevLauncher (iou=True) on (N,5) [x1,y1,x2,y2,ry] boxes."""
+    out = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    torch.cuda.synchronize()
+    fn = _load().ref_boxes_iou_bev if iou else _load().ref_boxes_overlap_bev
+    fn(boxes_a.shape[0], _p(boxes_a), boxes_b.shape[0], _p(boxes_b), _p(out))
+    torch.cuda.synchronize()
+    return out
+
+
+def nms(boxes, thresh, rotated=True):
+    """The reference's nms_gpu / nms_normal_gpu on score-sorted boxes: its mask kernel, then the host loop of
+    iou3d.cpp:100-113 replayed on the copied mask.  Returns the kept indices (int64, host)."""
+    import numpy as np
+    n = boxes.shape[0]
+    col_blocks = (n + 63) // 64
+    mask = torch.zeros((n, col_blocks), dtype=torch.int64, device=boxes.device)
+    torch.cuda.synchronize()
+    (_load().ref_nms_mask if rotated else _load().ref_nms_normal_mask)(_p(boxes), _p(mask), n, float(thresh))
+    torch.cuda.synchronize()
+    m = mask.cpu().numpy().view(np.uint64)
+    remv = np.zeros(col_blocks, dtype=np.uint64)
+    keep = []
+    for i in range(n):
+        nblock, inblock = divmod(i, 64)
+        if not (int(remv[nblock]) >> inblock) & 1:
+            keep.append(i)
+            remv[nblock:] |= m[i, nblock:]
+    return torch.tensor(keep, dtype=torch.int64)

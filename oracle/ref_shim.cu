@@ -45,3 +45,18 @@ void roipool3dLauncher(int batch_size, int pts_num, int boxes_num, int feature_i
 REF_API void ref_roipool3d(int b, int n, int m, int c, int sampled, const float *xyz, const float *boxes3d, const float *pts_feature,
                            float *pooled_features, int *pooled_empty_flag)
 { roipool3dLauncher(b, n, m, c, sampled, xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag); }
+
+// lib/utils/iou3d/src/iou3d_kernel.cu:352-387 (declared in iou3d.cpp:22-25): legacy default stream.  The host half of the
+// reference's nms_gpu (mask D2H + greedy loop, iou3d.cpp:95-113) is replayed by oracle/ref_cuda.py on the mask these produce.
+void boxesoverlapLauncher(const int num_a, const float *boxes_a, const int num_b, const float *boxes_b, float *ans_overlap);
+void boxesioubevLauncher(const int num_a, const float *boxes_a, const int num_b, const float *boxes_b, float *ans_iou);
+void nmsLauncher(const float *boxes, unsigned long long *mask, int boxes_num, float nms_overlap_thresh);
+void nmsNormalLauncher(const float *boxes, unsigned long long *mask, int boxes_num, float nms_overlap_thresh);
+REF_API void ref_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_overlap)
+{ boxesoverlapLauncher(num_a, boxes_a, num_b, boxes_b, ans_overlap); }
+REF_API void ref_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_iou)
+{ boxesioubevLauncher(num_a, boxes_a, num_b, boxes_b, ans_iou); }
+REF_API void ref_nms_mask(const float *boxes, unsigned long long *mask, int boxes_num, float thresh)
+{ nmsLauncher(boxes, mask, boxes_num, thresh); }
+REF_API void ref_nms_normal_mask(const float *boxes, unsigned long long *mask, int boxes_num, float thresh)
+{ nmsNormalLauncher(boxes, mask, boxes_num, thresh); }

@@ -1,0 +1,302 @@
+"""Rotated BEV overlap / IoU / NMS.
+
+CPU: the C oracle (a restatement of /root/reference/lib/utils/iou3d/src/iou3d_kernel.cu + the host loop of iou3d.cpp) against
+an independent float64 polygon clipper and analytic cases.  GPU: the B200 kernels against the reference's own, unmodified
+kernels (oracle/_ref) -- overlaps, IoUs and keep-sets bit for bit -- and against the oracle (floats to 1e-5 of the box scale:
+cosf/sinf/atan2f are libm on the CPU and libdevice on the GPU)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+
+def proposals(seed, n, spread=0.35, objects=None, jitter_seed=None):
+    """RPN-like BEV proposals: clusters of jittered car-sized boxes around `objects` centres in the KITTI x-z scope.
+    The object centres depend on `seed` and `objects` only, so two calls can populate the same scene."""
+    rng = np.random.RandomState(seed)
+    objects = objects or max(1, n // 40)
+    centres = np.stack([rng.uniform(-40, 40, objects), rng.uniform(0, 70.4, objects)], axis=1)
+    heading = rng.uniform(-np.pi, np.pi, objects)
+    rng = np.random.RandomState(seed + 7919 if jitter_seed is None else jitter_seed)
+    which = rng.randint(0, objects, n)
+    cx = centres[which, 0] + rng.randn(n) * spread
+    cz = centres[which, 1] + rng.randn(n) * spread
+    length = 3.9 + rng.randn(n) * 0.4
+    width = 1.6 + rng.randn(n) * 0.15
+    ry = heading[which] + rng.randn(n) * 0.15
+    flip = rng.rand(n) < 0.1
+    ry = np.where(flip, ry + np.pi / 2, ry)
+    b = np.stack([cx - length / 2, cz - width / 2, cx + length / 2, cz + width / 2, ry], axis=1).astype(np.float32)
+    return b
+
+
+def special_boxes():
+    """Degenerate and boundary configurations the clipping code has branches for."""
+    q = np.float32(np.pi / 2)
+    return np.array([
+        [0, 0, 4, 2, 0],            # axis aligned
+        [0, 0, 4, 2, 0],            # exact duplicate (collinear edges: no proper crossing, all corners inside)
+        [0, 0, 4, 2, np.pi],        # same rectangle turned by pi
+        [1, -1, 3, 3, q],           # the same rectangle as the first, expressed with a quarter turn
+        [4, 0, 8, 2, 0],            # shares an edge with the first
+        [4, 2, 6, 4, 0],            # shares a corner with the first
+        [1, 0.5, 2, 1.5, 0.3],      # fully inside the first
+        [-3, -3, 7, 5, -0.2],       # contains the first
+        [2, 1, 2, 1, 0.7],          # zero-size box
+        [0, 0, 4, 0, 0.1],          # zero width
+        [0, 0, 4, 2, 1e-4],         # almost parallel edges (the |s5 - s1| <= EPS branch region)
+        [0.5, 0.5, 4.5, 2.5, np.pi / 4],
+        [1000, 1000, 1004, 1002, 0.5],   # far away
+        [1000.5, 1000.2, 1004.5, 1002.2, 0.6],  # overlaps the previous one at large coordinates
+        [0, 0, 4, 2, 100.0],        # large angle: slow-path argument reduction of sinf/cosf
+        [0, 0, 4, 2, -7.5],
+    ], dtype=np.float32)
+
+
+# ---- an independent statement of the geometry: float64 Sutherland-Hodgman clipping ------------------------------------------
+
+def _corners64(b):
+    x1, y1, x2, y2, a = [float(v) for v in b]
+    cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+    c, s = np.cos(a), np.sin(a)
+    pts = []
+    for px, py in ((x1, y1), (x2, y1), (x2, y2), (x1, y2)):
+        dx, dy = px - cx, py - cy
+        pts.append((dx * c + dy * s + cx, -dx * s + dy * c + cy))
+    return pts
+
+
+def _area(poly):
+    return 0.5 * sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1] for i in range(len(poly)))
+
+
+def clip_area64(a, b):
+    subject, clip = _corners64(a), _corners64(b)
+    if abs(_area(subject)) < 1e-12 or abs(_area(clip)) < 1e-12:
+        return 0.0
+    if _area(clip) < 0:
+        clip = clip[::-1]
+    out = subject
+    for i in range(4):
+        p, q = clip[i], clip[(i + 1) % 4]
+        side = lambda r: (q[0] - p[0]) * (r[1] - p[1]) - (q[1] - p[1]) * (r[0] - p[0])  # noqa: E731
+        src, out = out, []
+        for k in range(len(src)):
+            cur, nxt = src[k], src[(k + 1) % len(src)]
+            sc, sn = side(cur), side(nxt)
+            if sc >= 0:
+                out.append(cur)
+            if (sc >= 0) != (sn >= 0):
+                t = sc / (sc - sn)
+                out.append((cur[0] + t * (nxt[0] - cur[0]), cur[1] + t * (nxt[1] - cur[1])))
+        if len(out) < 3:
+            return 0.0
+    return abs(_area(out))
+
+
+# ---- CPU: the oracle ---------------------------------------------------------------------------------------------------------
+
+def test_oracle_overlap_analytic():
+    b = special_boxes()
+    ov = oracle.boxes_overlap_bev(b, b)
+    assert ov[0, 0] == 8.0 and ov[0, 1] == 8.0            # duplicates: the eight contained corners
+    assert abs(ov[0, 2] - 8.0) < 1e-5 and abs(ov[0, 3] - 8.0) < 1e-5
+    assert ov[0, 4] < 1e-4 and ov[0, 5] < 1e-4            # shared edge / shared corner: (numerically) nothing
+    assert abs(ov[0, 6] - 1.0) < 1e-5 and abs(ov[6, 0] - 1.0) < 1e-5
+    assert abs(ov[0, 7] - 8.0) < 1e-5
+    assert ov[0, 8] == 0.0 and ov[0, 12] == 0.0
+    iou = oracle.boxes_iou_bev(b, b)
+    assert iou[0, 0] == 1.0 and abs(iou[0, 6] - 1.0 / 8.0) < 1e-6
+    # two unit squares, one turned by 45 degrees about the shared centre: a regular octagon
+    sq = np.array([[0, 0, 2, 2, 0], [0, 0, 2, 2, np.pi / 4]], dtype=np.float32)
+    assert abs(oracle.boxes_overlap_bev(sq, sq)[0, 1] - 8 * (np.sqrt(2) - 1)) < 1e-5
+
+
+def test_oracle_overlap_vs_float64_clipping():
+    b = np.concatenate([proposals(3, 90, objects=3), special_boxes()[:8]])
+    ov = oracle.boxes_overlap_bev(b, b)
+    ref = np.array([[clip_area64(x, y) for y in b] for x in b])
+    # the reference's method (vertices found separately, centre + atan2 ordering) loses accuracy only for slivers
+    assert np.abs(ov - ref).max() < 2e-3, np.abs(ov - ref).max()
+    big = ref > 0.5
+    assert (np.abs(ov - ref)[big] / ref[big]).max() < 1e-4
+    assert np.allclose(ov, ov.T, atol=1e-4)
+
+
+def test_oracle_iou_normal_and_nms():
+    b = proposals(5, 300)
+    iou_r, iou_n = oracle.boxes_iou_bev(b, b), oracle.boxes_iou_normal(b, b)
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    w = np.clip(np.minimum(x2[:, None], x2[None]) - np.maximum(x1[:, None], x1[None]), 0, None)
+    h = np.clip(np.minimum(y2[:, None], y2[None]) - np.maximum(y1[:, None], y1[None]), 0, None)
+    area = (x2 - x1) * (y2 - y1)
+    assert np.allclose(iou_n, w * h / np.maximum(area[:, None] + area[None] - w * h, 1e-8), rtol=1e-5, atol=1e-7)
+    for rotated, iou in ((True, iou_r), (False, iou_n)):
+        for thresh in (0.1, 0.5, 0.8):
+            keep = oracle.nms_bev(b, thresh, rotated)
+            removed, expect = np.zeros(len(b), bool), []
+            for i in range(len(b)):      # greedy scan stated on the full matrix
+                if not removed[i]:
+                    expect.append(i)
+                    removed[i + 1:] |= iou[i, i + 1:] > thresh
+            assert keep.tolist() == expect
+            assert len(keep) < len(b)
+    assert oracle.nms_bev(np.zeros((0, 5), np.float32), 0.5).size == 0
+    assert oracle.nms_bev(b[:1], 0.5).tolist() == [0]
+
+
+def test_python_surface_matches_reference_names():
+    # /root/reference/lib/utils/iou3d/iou3d_utils.py:6,21,56,73
+    from epnet_b200 import iou3d_utils
+    for n in ("boxes_iou_bev", "boxes_iou3d_gpu", "nms_gpu", "nms_normal_gpu"):
+        assert callable(getattr(iou3d_utils, n))
+    assert iou3d_utils.nms_workspace_bytes(2, 130) == 2 * 130 * 3 * 8
+    assert iou3d_utils.nms_workspace_bytes(0, 100) == 0
+    with pytest.raises(Exception):
+        iou3d_utils.boxes_iou_bev(torch.zeros(4, 5), torch.zeros(3, 5))    # CPU tensors are refused: no fallback
+
+
+def test_bad_arguments_reported():
+    from epnet_b200 import _lib
+    lib = _lib.LIB
+    assert lib.epnet_boxes_overlap_bev(-1, None, 0, None, None, None) == -1
+    assert lib.epnet_boxes_overlap_bev(0, None, 5, None, None, None) == 0
+    assert lib.epnet_nms_rotated(1, 10, None, None, 0.5, 0, None, None, None, None) == -1
+    assert lib.epnet_nms_normal(0, 10, None, None, 0.5, 0, None, None, None, None) == 0
+    assert lib.epnet_nms_workspace_bytes(1, 1, None) == -1
+
+
+# ---- GPU: product vs the reference's own kernels vs the oracle -----------------------------------------------------------------
+
+def _ref():
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_cuda
+
+
+def _bits(t):
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,m", [(1, 257, 130), (2, 700, 700), (3, 16, 1)])
+def test_pairwise_matches_reference_kernels_bit_for_bit(seed, n, m):
+    from epnet_b200 import iou3d_utils
+    ref = _ref()
+    a = np.concatenate([proposals(seed, n, objects=max(1, n // 60)), special_boxes()])
+    b = np.concatenate([special_boxes(), proposals(seed, m, objects=max(1, n // 60), jitter_seed=seed + 50)])   # same objects, other jitter
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    for fn, iou, orc in ((iou3d_utils.boxes_overlap_bev, False, oracle.boxes_overlap_bev), (iou3d_utils.boxes_iou_bev, True, oracle.boxes_iou_bev)):
+        ours, theirs = fn(ta, tb), ref.boxes_pairwise_bev(ta, tb, iou)
+        assert ours.shape == (len(a), len(b))
+        same = _bits(ours) == _bits(theirs)
+        bad = np.argwhere(~same)
+        assert same.all(), (len(bad), bad[:5], ours.cpu().numpy()[~same][:5], theirs.cpu().numpy()[~same][:5])
+        cpu = orc(a, b)
+        finite = np.isfinite(cpu)
+        scale = 8.0 if not iou else 1.0
+        assert np.abs(ours.cpu().numpy() - cpu)[finite].max() < 1e-4 * scale
+        assert (ours > 0).float().mean() > 0.01   # the case really exercises the clipping code
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 129, 1000, 4100])
+def test_nms_keep_sets_identical_to_reference(n):
+    from epnet_b200 import iou3d_utils
+    ref = _ref()
+    b = proposals(100 + n, n)
+    if n >= 64:
+        b[5:25] = special_boxes()[:16][np.arange(20) % 16]
+    tb = torch.from_numpy(b).cuda()
+    scores = torch.arange(n, 0, -1, dtype=torch.float32, device="cuda")      # already in score order
+    for rotated, mine in ((True, iou3d_utils.nms_gpu), (False, iou3d_utils.nms_normal_gpu)):
+        for thresh in (0.05, 0.5, 0.85):
+            theirs = ref.nms(tb, thresh, rotated)
+            ours = mine(tb, scores, thresh)
+            assert ours.dtype == torch.int64 and ours.is_cuda
+            assert ours.cpu().tolist() == theirs.tolist(), (rotated, thresh)
+            if n <= 1000:
+                cpu = oracle.nms_bev(b, thresh, rotated)
+                # libm vs libdevice can only flip a pair whose IoU sits within ~1e-6 of the threshold
+                assert len(set(cpu.tolist()) ^ set(ours.cpu().tolist())) <= max(1, n // 200)
+
+
+@pytest.mark.gpu
+def test_nms_scores_are_sorted_like_the_reference_wrapper():
+    from epnet_b200 import iou3d_utils
+    ref = _ref()
+    b = proposals(9, 900)
+    rng = np.random.RandomState(0)
+    scores = rng.rand(900).astype(np.float32)
+    tb, ts = torch.from_numpy(b).cuda(), torch.from_numpy(scores).cuda()
+    order = ts.sort(0, descending=True)[1]
+    theirs = order[ref.nms(tb[order].contiguous(), 0.7).cuda()]
+    ours = iou3d_utils.nms_gpu(tb, ts, 0.7)
+    assert ours.tolist() == theirs.tolist()
+    assert (ts[ours][:-1] >= ts[ours][1:]).all()
+
+
+@pytest.mark.gpu
+def test_nms_batched_counts_and_early_stop():
+    from epnet_b200 import iou3d_utils
+    ref = _ref()
+    S, N = 5, 700
+    counts = [700, 0, 1, 333, 64]
+    boxes = np.stack([proposals(40 + s, N) for s in range(S)])
+    tb = torch.from_numpy(boxes).cuda()
+    tc = torch.tensor(counts, dtype=torch.int32, device="cuda")
+    keep, num = iou3d_utils.nms_batched(tb, 0.6, counts=tc)
+    keep100, num100 = iou3d_utils.nms_batched(tb, 0.6, max_out=100, counts=tc)
+    ws = torch.empty(iou3d_utils.nms_workspace_bytes(S, N) // 8, dtype=torch.int64, device="cuda")
+    keep_n, num_n = iou3d_utils.nms_batched(tb, 0.6, counts=tc, rotated=False, workspace=ws)
+    for s in range(S):
+        theirs = ref.nms(tb[s, :counts[s]].contiguous(), 0.6).tolist() if counts[s] else []
+        assert int(num[s]) == len(theirs)
+        assert keep[s, :len(theirs)].tolist() == theirs
+        assert (keep[s, len(theirs):] == -1).all()
+        assert int(num100[s]) == min(100, len(theirs))
+        assert keep100[s, :int(num100[s])].tolist() == theirs[:100]
+        theirs_n = ref.nms(tb[s, :counts[s]].contiguous(), 0.6, rotated=False).tolist() if counts[s] else []
+        assert keep_n[s, :int(num_n[s])].tolist() == theirs_n
+    # sync-free single-problem form
+    scores = torch.rand(N, device="cuda")
+    idx, cnt = iou3d_utils.nms_fixed(tb[0], scores, 0.6, 50)
+    full = iou3d_utils.nms_gpu(tb[0], scores, 0.6)
+    assert int(cnt) == min(50, len(full)) and idx[:int(cnt)].tolist() == full[:50].tolist()
+    # empty problem sets
+    k0, n0 = iou3d_utils.nms_batched(torch.zeros((0, 8, 5), device="cuda"), 0.5)
+    assert k0.shape == (0, 8) and n0.numel() == 0
+    assert iou3d_utils.nms_gpu(torch.zeros((0, 5), device="cuda"), torch.zeros((0,), device="cuda"), 0.5).numel() == 0
+    assert iou3d_utils.boxes_iou_bev(torch.zeros((0, 5), device="cuda"), tb[0]).shape == (0, N)
+
+
+@pytest.mark.gpu
+def test_boxes_iou3d_matches_reference_composition():
+    from epnet_b200 import iou3d_utils
+    ref = _ref()
+    rng = np.random.RandomState(4)
+    n, m = 200, 150
+
+    def boxes3d(k, seed):
+        bev = proposals(seed, k, objects=4)
+        out = np.zeros((k, 7), np.float32)
+        out[:, 0], out[:, 2] = (bev[:, 0] + bev[:, 2]) / 2, (bev[:, 1] + bev[:, 3]) / 2
+        out[:, 5], out[:, 4] = bev[:, 2] - bev[:, 0], bev[:, 3] - bev[:, 1]
+        out[:, 3] = 1.5 + rng.rand(k) * 0.3
+        out[:, 1] = 1.7 + rng.randn(k) * 0.2
+        out[:, 6] = bev[:, 4]
+        return torch.from_numpy(out).cuda()
+
+    a, b = boxes3d(n, 11), boxes3d(m, 11)
+    ours = iou3d_utils.boxes_iou3d_gpu(a, b)
+    # iou3d_utils.py:21-53 with the reference's own overlap kernel
+    ov = ref.boxes_pairwise_bev(iou3d_utils.boxes3d_to_bev_torch(a).contiguous(), iou3d_utils.boxes3d_to_bev_torch(b).contiguous(), False)
+    a_min, a_max = (a[:, 1] - a[:, 3]).view(-1, 1), a[:, 1].view(-1, 1)
+    b_min, b_max = (b[:, 1] - b[:, 3]).view(1, -1), b[:, 1].view(1, -1)
+    o3 = ov * torch.clamp(torch.min(a_max, b_max) - torch.max(a_min, b_min), min=0)
+    va, vb = (a[:, 3] * a[:, 4] * a[:, 5]).view(-1, 1), (b[:, 3] * b[:, 4] * b[:, 5]).view(1, -1)
+    theirs = o3 / torch.clamp(va + vb - o3, min=1e-7)
+    assert torch.equal(ours, theirs)
+    assert ours.max() <= 1.0 + 1e-5 and (ours > 0.3).any()
