@@ -271,6 +271,7 @@ nms_scan_kernel(int nmax, const int *__restrict__ counts, const unsigned long lo
     extern __shared__ unsigned long long removed[];   // one bit per box of this problem
     __shared__ unsigned long long diag[kNmsTile];
     __shared__ unsigned long long kept_word;
+    __shared__ int kept_rows[kNmsTile];
 
     const int seg = blockIdx.x, t = threadIdx.x;
     const int n = counts ? min(max(__ldg(counts + seg), 0), nmax) : nmax;
@@ -284,30 +285,54 @@ nms_scan_kernel(int nmax, const int *__restrict__ counts, const unsigned long lo
     __syncthreads();
     for (int tile = 0; tile < tiles && kept < limit; ++tile) {
         const int base = tile * kNmsTile, size = min(kNmsTile, n - base);
-        if (t < kNmsTile) diag[t] = t < size ? mask[(size_t)(base + t) * stride + tile] : 0ULL;
+        if (t < kNmsTile) diag[t] = t < size ? __ldg(mask + (size_t)(base + t) * stride + tile) : 0ULL;
         __syncthreads();
         if (t == 0) {
-            unsigned long long r = removed[tile], kw = 0;
-            for (int i = 0; i < size; ++i)
-                if (!((r >> i) & 1ULL)) kw |= 1ULL << i, r |= diag[i];
+            // boxes of this tile in index order; only the survivors cost an iteration
+            const unsigned long long valid = size == kNmsTile ? ~0ULL : ((1ULL << size) - 1ULL);
+            unsigned long long r = removed[tile], kw = 0, cand = ~r & valid;
+            while (cand) {
+                const int i = __ffsll((long long)cand) - 1;
+                kw |= 1ULL << i;
+                r |= diag[i];
+                cand &= ~r & ~((2ULL << i) - 1ULL);
+            }
             kept_word = kw;
         }
         __syncthreads();
         const unsigned long long kw = kept_word;
+        const int kc = __popcll(kw);
         if (t < kNmsTile && ((kw >> t) & 1ULL)) {
-            const int pos = kept + __popcll(kw & ((1ULL << t) - 1ULL));
-            if (pos < limit) keep[pos] = base + t;
+            const int rank = __popcll(kw & ((1ULL << t) - 1ULL));
+            kept_rows[rank] = base + t;
+            if (kept + rank < limit) keep[kept + rank] = base + t;
         }
-        for (int j = tile + 1 + t; j < tiles; j += kReduceThreads) {
-            unsigned long long acc = removed[j], bits = kw;
-            while (bits) {
-                const int i = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                acc |= mask[(size_t)(base + i) * stride + j];
+        kept += kc;
+        __syncthreads();
+        // suppression words of the kept rows for the tiles still to come: (row, word) pairs dealt to all threads, loads in
+        // flight four at a time, the (mostly zero) words OR-ed into shared memory
+        const int rem = tiles - tile - 1;
+        if (rem > 0 && kept < limit) {
+            const int total = kc * rem;
+            for (int e = t; e < total; e += 4 * kReduceThreads) {
+                unsigned long long v[4];
+                int w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ee = e + u * kReduceThreads;
+                    v[u] = 0;
+                    w[u] = 0;
+                    if (ee < total) {
+                        const int r = ee / rem;
+                        w[u] = tile + 1 + (ee - r * rem);
+                        v[u] = __ldg(mask + (size_t)kept_rows[r] * stride + w[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (v[u]) atomicOr(&removed[w[u]], v[u]);
             }
-            removed[j] = acc;
         }
-        kept += __popcll(kw);
         __syncthreads();
     }
     if (t == 0) num_out[seg] = min(kept, limit);
