@@ -1,7 +1,16 @@
-"""Diagnostic: dump the product's and the reference kernels' pairwise BEV overlaps for one seeded case (run on the GPU box)."""
+"""Generates the data behind tests/golden/iou3d_ref_b200.npz: pairwise rotated BEV overlaps and IoUs of one seeded case computed
+by the REFERENCE'S OWN, unmodified kernels (oracle/_ref, built from /root/reference/lib/utils/iou3d/src/iou3d_kernel.cu) on a
+B200.  Run on the GPU box:
+
+    gpurun -- python tests/golden/make_iou3d_golden.py      # writes gpurun_out/iou3d_dump.npz (also holds the product's outputs)
+
+then keep a, b, ov_ref, iou_ref:  np.savez_compressed("tests/golden/iou3d_ref_b200.npz", ...).  The fixture lets the CPU suite
+check the C oracle against real reference outputs, and the GPU suite check the product bit for bit without oracle/_ref.
+"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 from test_iou3d import proposals, special_boxes
