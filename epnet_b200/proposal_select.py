@@ -10,7 +10,7 @@ keep the first 70 % / 30 % of RPN_PRE_NMS_TOP_N of each band (an empty far band 
 Here every step is a batched tensor op: ranks inside a band come from a cumulative sum of the band mask, the selected proposals
 are scattered into a padded (B, pre_n, 7) block with per-scene counts, ONE `nms_batched` launch per band handles all scenes and
 stops at the band's post-NMS quota, and the survivors are scattered to their final rows.  Outputs are identical to the
-reference's (same proposals, same order, zero padding) -- tests/test_proposal_select.py checks this against a literal
+reference's (same proposals, same order, zero padding) -- tests/test_zz_proposal_select.py checks this against a literal
 restatement of the reference loop.
 
 Box decoding (`decode_bbox_target`) and the network heads are out of scope (only the NMS row and its caller's
