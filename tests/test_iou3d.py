@@ -124,6 +124,29 @@ def test_oracle_overlap_vs_float64_clipping():
     assert np.allclose(ov, ov.T, atol=1e-4)
 
 
+def test_oracle_overlap_properties():
+    """Size-independent properties of the geometry on many random pairs: symmetry, bounded by the smaller box, rigid-motion
+    invariance (up to the rounding of the moved coordinates), IoU in [0, 1]."""
+    rng = np.random.RandomState(11)
+    n = 400
+    c = rng.uniform(-5, 5, size=(n, 2))
+    sz = rng.uniform(0.3, 6.0, size=(n, 2))
+    b = np.concatenate([c - sz / 2, c + sz / 2, rng.uniform(-7, 7, size=(n, 1))], axis=1).astype(np.float32)
+    ov = oracle.boxes_overlap_bev(b, b)
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    assert np.abs(ov - ov.T).max() < 5e-4
+    assert (ov <= np.minimum(area[:, None], area[None]) + 1e-3).all() and (ov >= 0).all()
+    assert np.abs(np.diag(ov) - area).max() < 1e-4 * area.max()
+    iou = oracle.boxes_iou_bev(b, b)
+    assert (iou >= 0).all() and (iou <= 1 + 1e-5).all()
+    # translate everything and turn every box by pi (a rectangle is symmetric under a half turn)
+    moved = b.copy()
+    moved[:, [0, 2]] += 16.0
+    moved[:, [1, 3]] -= 8.0
+    moved[:, 4] += np.float32(np.pi)
+    assert np.abs(oracle.boxes_overlap_bev(moved, moved) - ov).max() < 2e-3
+
+
 def test_oracle_iou_normal_and_nms():
     b = proposals(5, 300)
     iou_r, iou_n = oracle.boxes_iou_bev(b, b), oracle.boxes_iou_normal(b, b)
