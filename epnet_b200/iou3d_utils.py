@@ -101,7 +101,10 @@ def nms_fixed(boxes, scores, thresh, max_out, rotated=True):
     order = scores.sort(0, descending=True)[1]
     keep, num_out = nms_batched(boxes[order].unsqueeze(0), thresh, max_out=max_out, rotated=rotated)
     keep = keep[0, :max_out]
-    return torch.where(keep >= 0, order[keep.clamp(min=0)], keep), num_out[0]
+    idx = torch.where(keep >= 0, order[keep.clamp(min=0)], keep) if keep.numel() else keep
+    if idx.numel() < max_out:    # fewer boxes than max_out: pad to the promised length
+        idx = torch.cat([idx, idx.new_full((max_out - idx.numel(),), -1)])
+    return idx, num_out[0]
 
 
 def _nms(boxes, scores, thresh, rotated):
