@@ -268,6 +268,15 @@ def measure(model, runner, dev_pool, device, world):
                         "frac": round(e["bytes"] / e["time"] / 1e9 / peak, 5)})
         if e.get("tests"):  # the real bound of the search kernels is the fp32 distance-test rate, not bytes
             row["distance_tests_per_s"] = round(e["tests"] / e["time"], -9)
+        # the bytes roofline is reported for every non-GEMM kernel, but it is not what limits these
+        real_bound = {"fps_sample": "latency per iteration (M-1 serially dependent arg-max steps on one SM per scene): see fps_ns_per_iteration",
+                      "furthest_point_sampling": "latency per iteration: see fps_ns_per_iteration",
+                      "bucket_cloud": "latency (one CTA per scene sorts the cloud in shared memory, beside the FPS chain)",
+                      "ball_query": "fp32 distance tests: see distance_tests_per_s", "ball_query_sorted": "fp32 distance tests on the overlapping buckets",
+                      "three_nn": "fp32 distance tests: see distance_tests_per_s",
+                      "three_nn_weights": "fp32 distance tests: see distance_tests_per_s"}.get(name)
+        if real_bound:
+            row["real_bound"] = real_bound
         per_kernel.append(row)
     top = dict(per_kernel[0])
     traffic = None
