@@ -212,6 +212,14 @@ def test_python_surface_matches_reference_names():
     assert iou3d_utils.nms_workspace_bytes(0, 100) == 0
     with pytest.raises(Exception):
         iou3d_utils.boxes_iou_bev(torch.zeros(4, 5), torch.zeros(3, 5))    # CPU tensors are refused: no fallback
+    with pytest.raises(Exception):
+        iou3d_utils.nms_gpu(torch.zeros(4, 5), torch.zeros(4), 0.5)
+    with pytest.raises(ValueError):
+        iou3d_utils.nms_batched(torch.zeros(4, 5), 0.5)                    # (S, N, 5) expected
+    with pytest.raises(ValueError):
+        iou3d_utils.boxes_iou_bev(torch.zeros(4, 7), torch.zeros(3, 5))    # BEV boxes have 5 columns
+    bev = iou3d_utils.boxes3d_to_bev_torch(torch.tensor([[1.0, 2.0, 3.0, 1.5, 1.6, 4.0, 0.3]]))
+    assert torch.allclose(bev, torch.tensor([[-1.0, 2.2, 3.0, 3.8, 0.3]]))  # kitti_utils.py:137-150: x -+ l/2, z -+ w/2, ry
 
 
 def test_bad_arguments_reported():
