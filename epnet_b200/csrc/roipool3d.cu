@@ -9,7 +9,8 @@
 // index order), the per-warp hit lists are concatenated in shared memory, and the same CTA copies the selected rows
 // (lane-strided: coalesced reads of the point-major (B,N,C) features and coalesced writes).
 // The in-box test reproduces the reference's arithmetic as compiled by nvcc -O2 (PTX-checked): cosf/sinf of the box angle,
-// x_rot = dx*cosa - dz*sina (two products, no FMA), z_rot = fma(dz, cosa, dx*sina), |dx|,|dz| pre-test against 10 m.
+// x_rot = fma(dx, cosa, -(dz*sina)), z_rot = fma(dz, cosa, dx*sina), |dx|,|dz| pre-test against 10 m.  (x_rot is read off the SASS of
+// the reference build: its PTX shows mul, mul, sub without rounding modifiers, which ptxas contracts -- see csrc/iou3d.cu.)
 #include "common.cuh"
 
 namespace epnet {
@@ -47,7 +48,7 @@ roipool3d_kernel(int n, int m, int c, int sampled, const float *__restrict__ xyz
             const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
             const float dx = __fsub_rn(x, cx), dz = __fsub_rn(z, cz);
             if (!(fabsf(dx) > 10.0f) && !(fabsf(__fsub_rn(y, cy)) > half_h) && !(fabsf(dz) > 10.0f)) {
-                const float x_rot = __fsub_rn(__fmul_rn(dx, cosa), __fmul_rn(dz, sina));
+                const float x_rot = __fmaf_rn(dx, cosa, -__fmul_rn(dz, sina));
                 const float z_rot = __fmaf_rn(dz, cosa, __fmul_rn(dx, sina));
                 in = (x_rot >= -half_l) & (x_rot <= half_l) & (z_rot >= -half_w) & (z_rot <= half_w);
             }

@@ -300,7 +300,8 @@ ORACLE_API void oracle_grid_gather_bilinear_grad(int b, int c, int h, int w, int
  * /root/reference/lib/utils/roipool3d/src/roipool3d_kernel.cu: pt_in_box3d (:14-28), assign_pts_to_box3d (:97-120),
  * get_pooled_idx (:123-160: first `sampled` inside points in index order, cyclic repetition k % cnt, empty flag) and the copy
  * (:163-195).  Arithmetic as nvcc -O2 compiles it (PTX-checked): the double-typed literals only widen exactly-representable
- * halves, so float compares are equivalent; x_rot is two products and a subtraction (no FMA), z_rot one product and one FMA.
+ * halves, so float compares are equivalent; x_rot = fma(dx, cosa, -(dz*sina)) and z_rot = fma(dz, cosa, dx*sina) (the PTX shows x_rot as
+ * mul, mul, sub without rounding modifiers; ptxas contracts it -- read off the SASS).
  * cosf/sinf come from the C library here and from libdevice on the GPU: they can differ in the last bit, which can only flip
  * a point lying within ~1 ulp of a box face; tests compare this oracle with the reference kernel on the same inputs. */
 static int oracle_pt_in_box3d(float x, float y, float z, const float *box)
@@ -311,8 +312,8 @@ static int oracle_pt_in_box3d(float x, float y, float z, const float *box)
     const float dx = x - cx, dz = z - cz;
     if (fabsf(dx) > 10.0f || fabsf(y - cy) > half_h || fabsf(dz) > 10.0f) return 0;
     const float cosa = cosf(angle), sina = sinf(angle);
-    const float p0 = dx * cosa, p1 = dz * sina;
-    const float x_rot = p0 - p1;
+    const float p1 = dz * sina;
+    const float x_rot = fmaf(dx, cosa, -p1);   /* SASS of the reference build: FMUL dz*sina, FFMA dx*cosa - that */
     const float z_rot = fmaf(dz, cosa, dx * sina);
     return (x_rot >= -half_l) & (x_rot <= half_l) & (z_rot >= -half_w) & (z_rot <= half_w);
 }
