@@ -10,9 +10,10 @@ random-init weights (torch.manual_seed(0)).  Prints ONE JSON line on rank 0.
           finds its inputs in L2), device-timed with CUDA events, max over ranks.
   e2e   : scenes/s through the public module call with HOST (pinned) inputs: H2D of points/image/xy and
           D2H of the (B,128,N) features + xyz inside the timed region.
---impl reference runs the same network, weights, inputs and precision on the reference's OWN CUDA kernels
-(oracle/_ref/libpointnet2_ref.so built from the unmodified sources) in the reference's op-by-op composition,
-with ATen's grid_sample -- the "reference CUDA extension on the same B200" baseline of BASELINE.json.
+--impl reference (baseline/ref_arm.py) runs the UNMODIFIED reference: its own lib/net/pointnet2_msg.py::Pointnet2MSG over its
+own pointnet2_modules / pointnet2_utils (staged byte for byte under baseline/_ref), its own CUDA kernels
+(oracle/_ref/libpointnet2_ref.so built from the unmodified sources) and ATen's grid_sample -- the "reference CUDA
+extension on the same B200" baseline of BASELINE.json.  That arm never imports epnet_b200.
 """
 import argparse
 import json
@@ -29,6 +30,11 @@ sys.path.insert(0, ROOT)
 
 BATCH_PER_GPU = 2
 NPOINTS = 16384
+# what the arithmetic is: fp32 in, fp32 out, fp32 accumulation; the GEMM/convolution products are formed on the tensor cores
+# from two-term operand splits that carry 22 significand bits (tcgen05 has no fp32 MMA), everything else is plain fp32
+DTYPE = "f32 (GEMMs: fp32 operands split into 2xFP16 / 2xTF32 terms, 3 tensor-core MMAs per product, fp32 accumulate; <=1e-5 of fp32)"
+WORKLOAD = ("BASELINE.json configs[1]: EPNet RPN backbone forward, batch 2 per GPU, 16384 pts, 384x1280 image, "
+            "LI-Fusion + image attention, eval-mode BN, random-init weights")
 POOL = 24  # resident input batches rotated through: 24 x 12.4 MB = 298 MB > 126 MB L2
 
 
@@ -81,21 +87,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- models
-def build_model(impl, device):
+def build_model(device):
     from epnet_b200 import BackboneConfig, Pointnet2MSG
     torch.manual_seed(0)
-    if impl == "ours":
-        model = Pointnet2MSG(config=BackboneConfig())
-        model.auto_fast_inference = False  # bench.py drives the runner explicitly (pipelined); --no-graph times the module path
-    else:
-        from epnet_b200.pointnet2_utils import make_ops
-        from oracle import ref_cuda
-        ops = make_ops(ref_cuda)
-
-        def aten_gather(fm, xy):  # the reference's Feature_Gather, verbatim semantics (pointnet2_msg.py:107-120)
-            return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
-
-        model = Pointnet2MSG(config=BackboneConfig(), ops=ops, feature_gather=aten_gather, reference_composition=True)
+    model = Pointnet2MSG(config=BackboneConfig())
+    model.auto_fast_inference = False  # bench.py drives the runner explicitly (pipelined); --no-graph times the module path
     return model.to(device).eval()
 
 
@@ -120,7 +116,7 @@ def timed_region(fn, steps, rank_sync, drain=None):
     return start.elapsed_time(end)  # ms
 
 
-def cpu_baseline_leg(sample_scenes=1):
+def cpu_baseline_leg(sample_scenes=1, budget_s=15.0):
     """Pure-PyTorch CPU implementation of the same backbone (oracle/torch_cpu.py ops + torch CPU convs) on
     `sample_scenes` scene(s) of the workload, all host cores."""
     from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
@@ -137,12 +133,16 @@ def cpu_baseline_leg(sample_scenes=1):
                          reference_composition=True).eval()
     data = scenes.batch(1000, sample_scenes, NPOINTS)
     with torch.no_grad():
-        t0 = time.perf_counter()
-        model(data["points"], data["image"], data["xy"].clone())
-        dt = time.perf_counter() - t0
+        model(data["points"], data["image"], data["xy"].clone())  # warm-up: thread pool, oneDNN primitive caches, allocator
+        runs, t0 = 0, time.perf_counter()
+        while runs < 12 and (runs < 3 or time.perf_counter() - t0 < budget_s):
+            model(data["points"], data["image"], data["xy"].clone())
+            runs += 1
+        dt = (time.perf_counter() - t0) / runs
     return {"value": round(sample_scenes / dt, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
-            "sample": "%d scene(s) of the batch, one full backbone forward, pure-PyTorch CPU ops (oracle/torch_cpu.py)" % sample_scenes,
-            "seconds": round(dt, 2)}
+            "sample": "%d scene(s) of the batch: 1 warm-up + %d timed full backbone forwards (mean), pure-PyTorch CPU ops "
+                      "(oracle/torch_cpu.py) + torch CPU convolutions, all host cores" % (sample_scenes, runs),
+            "seconds_per_forward": round(dt, 3)}
 
 
 def main():
@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 in cuDNN/cuBLAS (default 0: strict fp32 in both arms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency-leg", action="store_true", help="skip the one-batch-at-a-time measurement")
     ap.add_argument("--no-graph", action="store_true", help="ours: run eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--pipeline", type=int, default=8, help="ours: batches kept in flight (PipelinedRunner depth; 1 = one at a time)")
     ap.add_argument("--layout", choices=["pm", "cm"], default="pm")
@@ -171,22 +172,33 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
-    torch.backends.cudnn.benchmark = True
 
     def rank_sync():
         if distributed:
             dist.barrier()
 
+    if args.impl == "reference":
+        # the unmodified reference through its own public API; nothing of epnet_b200 is imported in this process
+        from baseline import ref_arm
+        ref_arm.run(args, world, rank, local_rank, distributed, device,
+                    {"ClockSampler": ClockSampler, "timed_region": timed_region, "rank_sync": rank_sync, "BATCH_PER_GPU": BATCH_PER_GPU,
+                     "NPOINTS": NPOINTS, "POOL": POOL, "WORKLOAD": WORKLOAD})
+        if distributed:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = True
     from epnet_b200 import pointnet2_cuda
-    model = build_model(args.impl, device)
+    model = build_model(device)
     host_pool = make_pool(POOL, 1000 + 1000 * rank)
     dev_pool = [{k: v.to(device) for k, v in b.items()} for b in host_pool]
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_pool[:4]]
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
 
-    use_graph = args.impl == "ours" and not args.no_graph and args.mode == "infer"
+    use_graph = not args.no_graph and args.mode == "infer"
     runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device, layout=args.layout, pipeline=args.pipeline) if use_graph else None
     depth = args.pipeline if runner is not None else 1
 
@@ -288,9 +300,8 @@ def main():
                   "RPN backbone training scenes/s (forward+backward+Adam, train-mode BN, DDP all-reduce, 16384 pts + 384x1280 image)",
         "value": round(scenes_total / (ms / 1e3), 3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: EPNet RPN backbone forward, batch 2 per GPU, 16384 pts, "
-                               "384x1280 image, LI-Fusion + image attention, eval-mode BN, random-init weights",
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE if args.mode == "infer" and runner is not None else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": BATCH_PER_GPU, "npoints": NPOINTS, "tf32": bool(args.tf32),
                    "l2": "inputs rotate over a %d-batch resident pool (%.0f MB > 126 MB L2)" % (POOL, POOL * h2d_bytes / 1e6),
                    "parallelism": "dp%d (independent scenes per GPU, no collective in the forward)" % world,
@@ -302,14 +313,24 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if args.impl == "reference":
-        line["impl"] = "reference"
-        line["cpu_baseline"] = {"value": line["value"], "unit": "scenes/s", "cores": 0, "kind": "reference",
-                                "sample": "not a CPU run: the reference's own pointnet2 CUDA kernels (unmodified sources compiled "
-                                          "for sm_100a into oracle/_ref) under the reference's op-by-op module composition and ATen "
-                                          "grid_sample, same B200, same inputs/weights/precision -- BASELINE.json's second baseline"}
+    if args.mode == "infer" and runner is not None and depth > 1 and not args.no_latency_leg:
+        # the same forward one batch at a time (graph replay, latency tile policy): what a caller that cannot keep several
+        # batches in flight gets; every rank runs it (same work), rank 0 reports its own figure
+        single = model.make_runner(BATCH_PER_GPU, NPOINTS, device, pipeline=1)
+        k1 = min(args.steps, 50)
 
-    if rank == 0 and args.impl == "ours" and args.mode == "infer":
+        def step_single(i):
+            b = dev_pool[i % len(dev_pool)]
+            return single(b["points"], b["image"], b["xy"])
+
+        for i in range(3):
+            step_single(i)
+        ms1 = timed_region(step_single, k1, rank_sync)
+        line["one_batch_at_a_time"] = {"value": round(BATCH_PER_GPU * k1 / (ms1 / 1e3), 3), "unit": "scenes/s per GPU",
+                                       "ms_per_step": round(ms1 / k1, 4), "steps": k1, "batches_in_flight": 1}
+        del single
+
+    if rank == 0 and args.mode == "infer":
         try:
             import bench_roofline
             line.update(bench_roofline.measure(model, runner, dev_pool, device, world))

@@ -19,12 +19,16 @@ def install(patch_grid_sample=True):
     """Make the UNCHANGED reference code run on these kernels.
 
     1. registers this package's `pointnet2_cuda` under that top-level name, which is what
-       pointnet2_lib/pointnet2/pointnet2_utils.py:7 imports;
+       pointnet2_lib/pointnet2/pointnet2_utils.py:7 imports (likewise `iou3d_cuda` and `roipool3d_cuda`);
     2. rebinds the module-global `grid_sample` of the reference backbone (lib/net/pointnet2_msg.py:6, used
        at :118; lib/net/rpn.py:9 imports that file as top-level `pointnet2_msg`) if it is already
        imported, and returns a function that does so for modules imported later.
     """
+    from . import iou3d_cuda, roipool3d_cuda
     sys.modules["pointnet2_cuda"] = pointnet2_cuda
+    # the two next-row extensions (SURVEY.md 8f): lib/utils/iou3d/iou3d_utils.py:2, lib/utils/roipool3d/roipool3d_utils.py:2
+    sys.modules["iou3d_cuda"] = iou3d_cuda
+    sys.modules["roipool3d_cuda"] = roipool3d_cuda
 
     def patch(module):
         module.grid_sample = li_fusion.grid_sample

@@ -8,7 +8,9 @@ import os
 
 import torch
 
-from . import REF_LIB_PATH
+# no relative import: baseline/ref_env.py loads this file by path (as `pointnet2_cuda`) without importing the oracle package,
+# so that the reference arm's process maps the reference's kernels and nothing else of this repo
+REF_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libpointnet2_ref.so")
 
 _c_int, _c_float, _c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -46,6 +48,10 @@ def _load():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = None
+        for name in ("ref_nms_gpu", "ref_nms_normal_gpu"):
+            fn = getattr(lib, name)
+            fn.argtypes = [_c_void_p, _c_void_p, _c_int, _c_float]
+            fn.restype = _c_int
         _lib = lib
     return _lib
 
@@ -149,3 +155,41 @@ def nms(boxes, thresh, rotated=True):
             keep.append(i)
             remv[nblock:] |= m[i, nblock:]
     return torch.tensor(keep, dtype=torch.int64)
+
+
+# ---- the pybind tables of the two next-row extensions, on the reference's own kernels (used by baseline/ref_env.py) ----
+
+class iou3d_cuda:  # lib/utils/iou3d/src/iou3d.cpp:172-177
+    @staticmethod
+    def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
+        torch.cuda.current_stream().synchronize()  # the reference launches on the legacy default stream
+        _load().ref_boxes_overlap_bev(boxes_a.shape[0], _p(boxes_a), boxes_b.shape[0], _p(boxes_b), _p(ans_overlap))
+        return 1
+
+    @staticmethod
+    def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
+        torch.cuda.current_stream().synchronize()
+        _load().ref_boxes_iou_bev(boxes_a.shape[0], _p(boxes_a), boxes_b.shape[0], _p(boxes_b), _p(ans_iou))
+        return 1
+
+    @staticmethod
+    def nms_gpu(boxes, keep, thresh):
+        assert not keep.is_cuda and keep.dtype == torch.int64 and keep.is_contiguous()
+        torch.cuda.current_stream().synchronize()
+        return _load().ref_nms_gpu(_p(boxes), keep.data_ptr(), boxes.shape[0], float(thresh))
+
+    @staticmethod
+    def nms_normal_gpu(boxes, keep, thresh):
+        assert not keep.is_cuda and keep.dtype == torch.int64 and keep.is_contiguous()
+        torch.cuda.current_stream().synchronize()
+        return _load().ref_nms_normal_gpu(_p(boxes), keep.data_ptr(), boxes.shape[0], float(thresh))
+
+
+class roipool3d_cuda:  # lib/utils/roipool3d/src/roipool3d.cpp:40-70
+    @staticmethod
+    def forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
+        b, n, m = xyz.shape[0], xyz.shape[1], boxes3d.shape[1]
+        torch.cuda.current_stream().synchronize()
+        _load().ref_roipool3d(b, n, m, pts_feature.shape[2], pooled_features.shape[2], _p(xyz), _p(boxes3d), _p(pts_feature),
+                              _p(pooled_features), _p(pooled_empty_flag))
+        return 1

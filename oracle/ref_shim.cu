@@ -60,3 +60,32 @@ REF_API void ref_nms_mask(const float *boxes, unsigned long long *mask, int boxe
 { nmsLauncher(boxes, mask, boxes_num, thresh); }
 REF_API void ref_nms_normal_mask(const float *boxes, unsigned long long *mask, int boxes_num, float thresh)
 { nmsNormalLauncher(boxes, mask, boxes_num, thresh); }
+
+// The reference's nms_gpu / nms_normal_gpu wrappers (iou3d.cpp:74-121, :124-170) need torch's C++ API (at::Tensor); their
+// bodies are restated here on raw pointers so the reference ARM pays what the reference pays: a cudaMalloc of the
+// N x ceil(N/64) mask, the reference's own mask kernel, a blocking D2H copy, the greedy host loop, a cudaFree.
+#include <cstring>
+#include <vector>
+static int ref_nms_host(const float *boxes, long long *keep, int n, float thresh, bool rotated)
+{
+    const int col_blocks = (n + 63) / 64;
+    unsigned long long *mask = nullptr;
+    if (cudaMalloc((void **)&mask, sizeof(unsigned long long) * (size_t)n * col_blocks) != cudaSuccess) return -1;
+    if (rotated) nmsLauncher(boxes, mask, n, thresh); else nmsNormalLauncher(boxes, mask, n, thresh);
+    std::vector<unsigned long long> mask_cpu((size_t)n * col_blocks);
+    cudaMemcpy(mask_cpu.data(), mask, sizeof(unsigned long long) * (size_t)n * col_blocks, cudaMemcpyDeviceToHost);
+    cudaFree(mask);
+    std::vector<unsigned long long> remv(col_blocks, 0ull);
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+        const int nblock = i / 64, inblock = i % 64;
+        if (!(remv[nblock] & (1ull << inblock))) {
+            keep[kept++] = i;
+            const unsigned long long *p = mask_cpu.data() + (size_t)i * col_blocks;
+            for (int j = nblock; j < col_blocks; ++j) remv[j] |= p[j];
+        }
+    }
+    return kept;
+}
+REF_API int ref_nms_gpu(const float *boxes, long long *keep, int n, float thresh) { return ref_nms_host(boxes, keep, n, thresh, true); }
+REF_API int ref_nms_normal_gpu(const float *boxes, long long *keep, int n, float thresh) { return ref_nms_host(boxes, keep, n, thresh, false); }
