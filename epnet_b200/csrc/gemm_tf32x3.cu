@@ -256,6 +256,14 @@ struct RowSource {
     }
 };
 
+// Range guard of the FP16 operand split: gemm_f16x3_kernel needs |x| < 65504.  Every value such a kernel can read is bounded by
+// a value some GEMM epilogue of this file wrote (activations of the previous layer; interpolation, bilinear gathering, max-pooling
+// and the sigmoid attention scale are convex combinations or contractions of them), so every epilogue raises this per-device flag
+// when it writes a magnitude above kF16Guard (or a non-finite value).  The host reads it after the forward
+// (epnet_gemm_overflow_read) and re-runs on the TF32 split, whose range is fp32's (epnet_b200/runner.py).
+__device__ unsigned int g_gemm_overflow = 0u;
+constexpr float kF16Guard = 6.0e4f;
+
 // Accumulator -> global memory: main + correction, bias, ReLU, then plain rows / pooled rows / the transposed convolution's
 // patch scatter.  Called by the four warps whose warp index selects the TMEM lane quarter (thread = lane = tile row).
 __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_acc, uint32_t corr_off, int warp, int lane, int row0,
@@ -265,6 +273,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
     const int r = warp * 32 + lane;  // TMEM lane == tile row
     const int row = row0 + r;
     const int pool = a.pool;
+    float amax = 0.f;
     for (int c0 = c_first; c0 < BN; c0 += c_step) {
         uint32_t v[32], w[32];
         const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
@@ -277,6 +286,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
         for (int j = 0; j < 32; ++j) {
             float f = __fmaf_rn(__uint_as_float(w[j]), a.corr_scale, __uint_as_float(v[j])) + bias_s[c0 + j];  // scale 1: an exact add
             if (a.relu) f = fmaxf(f, 0.f);
+            amax = fmaxf(amax, fabsf(f));  // padding rows/columns hold bias-only values: harmless
             v[j] = __float_as_uint(f);
         }
         if (a.tr) {
@@ -344,6 +354,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
             }
         }
     }
+    if (!(amax <= kF16Guard)) atomicOr(&g_gemm_overflow, 1u);  // also true for NaN/inf
 }
 
 __global__ void __launch_bounds__(kGmThreads, 2)
@@ -1122,4 +1133,19 @@ EPNET_API int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int c
                                       const float *bias, int relu, float *out, int ldo, void *stream)
 {
     return deconv_entry(1, b, h, w, cin, k, co, x, ldx, wpack, BN, bias, relu, out, ldo, stream);
+}
+
+// FP16-split range guard (see g_gemm_overflow): asynchronous read of the per-device flag into host memory (pinned for a truly
+// asynchronous copy) and reset, both ordered on `stream`.  No reference counterpart: the reference computes in fp32.
+EPNET_API int epnet_gemm_overflow_read(unsigned int *host_dst, void *stream)
+{
+    if (!host_dst) return EPNET_ERR_BAD_ARG;
+    return (int)cudaMemcpyFromSymbolAsync(host_dst, epnet::g_gemm_overflow, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+}
+EPNET_API int epnet_gemm_overflow_reset(void *stream)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(&p, epnet::g_gemm_overflow);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemsetAsync(p, 0, sizeof(unsigned int), (cudaStream_t)stream);
 }

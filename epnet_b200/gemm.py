@@ -16,9 +16,49 @@ BK = 32
 _TILE_POLICY = "latency"
 
 # Wide tiles (BN > 64) on the FP16 two-term split (csrc/gemm_tf32x3.cu, gemm_f16x3_kernel) instead of the TF32 split: same 22
-# significand bits, twice the MMA rate, half the operand bytes.  Needs |x|, |w| < 65504 (fp16 range).
+# significand bits, twice the MMA rate, half the operand bytes.  Needs |x|, |w| < 65504 (fp16 range).  Guards:
+#   * weights: a layer whose (folded) weights reach F16_LIMIT never takes the FP16 kernel (PackedLinear.f16_ok, checked at pack time);
+#   * activations: every GEMM epilogue raises a device flag when it writes |y| > 6e4 or a non-finite value (OverflowFlag below);
+#     the runner reads it with the result and re-runs on the TF32 split (range = fp32's) -- runner.py.
 F16_WIDE = _os.environ.get("EPNET_F16_WIDE", "1") != "0"
+F16_LIMIT = 6.0e4
 BK16 = 64
+
+
+@contextlib.contextmanager
+def f16_split(enabled):
+    """enable / disable the FP16-split kernels for the launches (and CUDA-graph captures) made inside the block"""
+    global F16_WIDE
+    prev, F16_WIDE = F16_WIDE, bool(enabled) and F16_WIDE
+    try:
+        yield
+    finally:
+        F16_WIDE = prev
+
+
+class OverflowFlag:
+    """Host view of the library's per-device range-guard flag (epnet_gemm_overflow_read / _reset)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    def read_async(self):
+        """enqueue flag -> pinned host word on the current stream of the device"""
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            from ._lib import check
+            check(LIB.epnet_gemm_overflow_read(self.host.data_ptr(), stream.cuda_stream), "gemm_overflow_read")
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            from ._lib import check
+            check(LIB.epnet_gemm_overflow_reset(torch.cuda.current_stream(self.device).cuda_stream), "gemm_overflow_reset")
+        self.host.zero_()
+
+    def value(self):
+        """the last value read (call after synchronising the stream read_async was issued on)"""
+        return int(self.host.item())
 
 
 @contextlib.contextmanager
@@ -62,6 +102,8 @@ class PackedLinear:
         self.n_kblocks = (self.K + BK - 1) // BK
         self._w = w
         self._packs = {}
+        # the FP16 split of the weights needs |w| < 65504 (h1 = fp16(w)); a layer outside that range stays on the TF32 split
+        self.f16_ok = bool(w.numel() == 0 or (w.abs().max() < F16_LIMIT).item())
         self.BN = choose_bn(self.N)
         self.wpack = self._pack(self.BN)
         self.bias = None if bias is None else bias.detach().float().contiguous()
@@ -106,7 +148,7 @@ class PackedLinear:
 
     def wide_f16(self, bn):
         """True when a launch with this column tile should take the FP16-split kernel"""
-        return F16_WIDE and bn > 64
+        return F16_WIDE and self.f16_ok and bn > 64
 
     def for_rows(self, rows):
         """(BN, packed weights) for a launch over `rows` rows: packed on first use per tile width, then cached (warm the shapes
@@ -116,7 +158,7 @@ class PackedLinear:
             # at most 4 k-blocks per tile: the per-tile cost is set-up and epilogue, which the persistent narrow-tile kernel
             # amortises (measured: transposed conv 128 -> 16 x 4 x 4, 83 -> 58 us), even though X is then read once per 64 columns
             bn = choose_bn(min(self.N, 128))
-        elif F16_WIDE and 64 < self.N <= 128 and self.K >= 512:
+        elif F16_WIDE and self.f16_ok and 64 < self.N <= 128 and self.K >= 512:
             # long-K layers with 65..128 columns (the 64->128 and 128->128 convolutions): one FP16-split tile instead of two narrow
             # TF32 tiles (235 -> 218 us, 133 -> 110 us); short-K layers of that width stay on the persistent narrow-tile kernel
             bn = (self.N + 15) // 16 * 16

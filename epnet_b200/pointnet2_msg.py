@@ -139,6 +139,7 @@ class Pointnet2MSG(nn.Module):
         # reference-style calling code gets the fast path without knowing about it (set False to force the module path)
         self.auto_fast_inference = True
         self._runner_cache = {}
+        self._f16_ok = True
         self._ops = ops or pointnet2_utils.OPS
         # (feature_map (B,C,H,W), xy (B,N,2)) -> (B,C,N); the LI-Fusion boundary
         self._feature_gather = feature_gather or (lambda fm, xy: li_fusion.feature_gather(fm, xy, c.align_corners))
@@ -181,15 +182,17 @@ class Pointnet2MSG(nn.Module):
             self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k]),
                                                     ops=self._ops))
 
-    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", pipeline=1):
+    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", pipeline=1, f16=True):
         """Inference fast path (eval mode): one CUDA graph with the FPS chain, the image stream and the point
-        stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py."""
+        stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py.
+        f16=False keeps every GEMM on the TF32 operand split (fp32 range; see BackboneRunner)."""
         if self.reference_composition:
             raise RuntimeError("reference_composition=True pins the op-by-op path")
         from .runner import BackboneRunner, PipelinedRunner
         if pipeline > 1:
-            return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, layout=layout)
-        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, layout=layout)
+            return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, layout=layout,
+                                   f16=f16)
+        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, layout=layout, f16=f16)
 
     @staticmethod
     def _break_up_pc(pc):
@@ -207,10 +210,20 @@ class Pointnet2MSG(nn.Module):
         stamp = self._state_stamp()
         entry = self._runner_cache.get(key)
         if entry is None or entry[0] != stamp:  # first call for this shape, or the weights changed since capture
+            self._f16_ok = True
             runner = self.make_runner(key[0], key[1], key[4], image_hw=(key[2], key[3]))
             entry = (self._state_stamp(), runner)
             self._runner_cache = {key: entry}
         xyz, feats = entry[1](pointcloud, image, xy)
+        if self._f16_ok and entry[1].overflowed():
+            # an activation left fp16's range (e.g. a checkpoint whose folded BatchNorm scales are huge): this input, and every later
+            # one, runs with the TF32 operand split, whose range is fp32's
+            self._f16_ok = False
+            entry[1].overflow.reset()
+            runner = self.make_runner(key[0], key[1], key[4], image_hw=(key[2], key[3]), f16=False)
+            entry = (stamp, runner)
+            self._runner_cache = {key: entry}
+            xyz, feats = runner(pointcloud, image, xy)
         xy[:, :, 0] = xy[:, :, 0] / (c.image_size[0] - 1.0) * 2.0 - 1.0  # the reference normalises the caller's xy in place
         xy[:, :, 1] = xy[:, :, 1] / (c.image_size[1] - 1.0) * 2.0 - 1.0
         return xyz.clone(), feats.clone()  # the runner owns its output buffers

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import pointnet2_cuda as pc
-from .gemm import PackedConv3x3, PackedDeconv, PackedLinear, grouped_first_layer, tile_policy
+from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -105,14 +105,20 @@ class _FusionPM:
         return self.fuse(cat, relu=True, out=out, out_cm=out_cm)
 
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency"):
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency", f16=True):
         """layout "pm": point-major activations + tcgen05 fp32-grade GEMMs (default); "cm": channel-major + cuBLAS.
-        The wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE): activations and folded weights must stay below
-        65504 in magnitude (they are below 10 for the published configuration); set EPNET_F16_WIDE=0 for the TF32 split.
+        f16: the wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE), which needs activations and folded weights
+        below 65504 in magnitude (they are below 10 for the published configuration).  Guarded twice: a layer whose folded
+        weights leave the range is packed for the TF32 split (PackedLinear.f16_ok), and every GEMM epilogue raises a device flag
+        on |y| > 6e4 / non-finite values, read back with every call (`overflowed()`); Pointnet2MSG.forward and PipelinedRunner
+        callers then switch to f16=False (TF32 split everywhere: fp32's range).  EPNET_F16_WIDE=0 forces that from the start.
         tiles: gemm.tile_policy for every GEMM launch of this runner ("latency" for one batch at a time)."""
         assert layout in ("pm", "cm")
         self.layout = layout
         self.tiles = tiles
+        self.f16 = bool(f16)
+        self.overflow = OverflowFlag(device)
+        self._last_stream = None
         if model.training:
             raise RuntimeError("BackboneRunner folds BatchNorm: call model.eval() first (train mode: use model(...) itself)")
         c = model.config
@@ -178,7 +184,7 @@ class BackboneRunner:
         return x
 
     def _forward(self):
-        with tile_policy(self.tiles):
+        with tile_policy(self.tiles), f16_split(self.f16):
             return self._forward_impl()
 
     def _forward_impl(self):
@@ -510,9 +516,22 @@ class BackboneRunner:
         self._load(points, image, xy)
         if self.graph is None:
             with torch.no_grad():
-                return self._forward()
-        self.graph.replay()
-        return self.out
+                out = self._forward()
+        else:
+            self.graph.replay()
+            out = self.out
+        self._last_stream = torch.cuda.current_stream(self.device)
+        self.overflow.read_async()  # 4 bytes, ordered after the forward on this stream
+        return out
+
+    def overflowed(self):
+        """True when a GEMM of ANY forward on this device since the last reset wrote a value an FP16-split layer cannot represent
+        (the flag is per device and sticky).  Synchronises with this runner's last call.  The results of such a forward are
+        not trustworthy when f16 is on: rebuild the runner with f16=False (after `overflow.reset()`) and run again."""
+        if self._last_stream is None:
+            return False
+        self._last_stream.synchronize()
+        return self.overflow.value() != 0
 
     def eager(self, points, image, xy, single_stream=False):
         """Same schedule without the graph (profiling: events around individual launches); single_stream=True also
@@ -554,6 +573,14 @@ class PipelinedRunner:
 
     def stream_of_last_call(self):
         return self.streams[(self.calls - 1) % len(self.runners)]
+
+    def overflowed(self):
+        """see BackboneRunner.overflowed; waits for every in-flight batch"""
+        return any([r.overflowed() for r in self.runners])
+
+    @property
+    def overflow(self):
+        return self.runners[0].overflow
 
     def join(self):
         """make the caller's current stream wait for every in-flight batch"""

@@ -153,6 +153,13 @@ int epnet_conv3x3_nhwc_f16x3(int b, int h, int w, int cin, int cout, int stride,
 int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
                             const float *bias, int relu, float *out, int ldo, void *stream);
 
+/* Range guard of the FP16 operand split (no reference counterpart: pytorch_utils.py:20-32 computes in fp32).  Every GEMM
+ * epilogue of this library raises a per-device flag when it writes a magnitude above 6e4 or a non-finite value -- i.e. whenever
+ * a following FP16-split layer could overflow.  _read copies the flag (0/1) to host memory asynchronously on `stream` (pinned
+ * memory for a truly asynchronous copy), _reset clears it on `stream`.  The caller re-runs on the TF32 split when it is set. */
+int epnet_gemm_overflow_read(unsigned int *host_dst, void *stream);
+int epnet_gemm_overflow_reset(void *stream);
+
 /* First shared-MLP layer of a set-abstraction scale with QueryAndGroup fused into the operand load (pointnet2_utils.py:241-264 +
  * pointnet2_modules.py:47-52): GEMM row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], 0..c) | xyz[scene, idx] -
  * new_xyz[scene, p]] is gathered straight into the tensor-core operand, the grouped tensor is never written.  feats point-major

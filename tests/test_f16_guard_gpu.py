@@ -1,0 +1,89 @@
+"""Range guard of the FP16 operand split (gemm_f16x3_kernel needs |x|, |w| < 65504):
+  * a layer whose weights leave the range is packed for the TF32 split and stays fp32-accurate;
+  * activations beyond 6e4 raise the device flag; Pointnet2MSG.forward then re-runs on the TF32 split and returns finite,
+    correct features -- the case of a trained checkpoint whose folded BatchNorm scales are large (tiny running variance)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_out_of_range_weights_take_the_tf32_split():
+    from epnet_b200 import gemm
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3000, 512, generator=g).cuda()
+    w = (torch.randn(256, 512, generator=g) * 1.0e5).cuda()  # |w| up to ~4e5: fp16 would be inf
+    lin = gemm.PackedLinear(w, None)
+    assert not lin.f16_ok
+    bn = lin.for_rows(3000)[0]
+    assert bn > 64 and not lin.wide_f16(bn)
+    y = lin(x, relu=False)
+    want = x.double() @ w.double().t()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y).all())
+    assert (y.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
+    small = gemm.PackedLinear(w * 1e-6, None)
+    assert small.f16_ok and small.wide_f16(small.for_rows(3000)[0]) == gemm.F16_WIDE
+
+
+def test_overflow_flag_is_raised_by_large_outputs_and_reset():
+    from epnet_b200 import gemm
+    dev = torch.device("cuda")
+    flag = gemm.OverflowFlag(dev)
+    flag.reset()
+    x = torch.ones(256, 64, device=dev)
+    lin = gemm.PackedLinear(torch.full((64, 64), 10.0, device=dev), None)
+    lin(x, relu=False)  # 640: fine
+    flag.read_async()
+    torch.cuda.synchronize()
+    assert flag.value() == 0
+    lin(x * 200.0, relu=False)  # 128000 > 6e4
+    flag.read_async()
+    torch.cuda.synchronize()
+    assert flag.value() == 1
+    lin(x, relu=False)  # sticky until reset
+    flag.read_async()
+    torch.cuda.synchronize()
+    assert flag.value() == 1
+    flag.reset()
+    flag.read_async()
+    torch.cuda.synchronize()
+    assert flag.value() == 0
+
+
+def test_backbone_falls_back_to_tf32_when_activations_leave_fp16_range():
+    from epnet_b200 import BackboneConfig, Pointnet2MSG, gemm, scenes
+    if not gemm.F16_WIDE:
+        pytest.skip("EPNET_F16_WIDE=0")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = Pointnet2MSG(config=BackboneConfig()).cuda().eval()
+    with torch.no_grad():  # a "trained" BatchNorm with a tiny running variance and a large gain: folded scale ~ 9e4
+        bn = model.Img_Block[2].bn1
+        bn.running_var.fill_(1e-6)
+        bn.weight.fill_(300.0)
+    gemm.OverflowFlag(torch.device("cuda")).reset()
+    data = {k: v.cuda() for k, v in scenes.batch(1000, 2, 16384).items()}
+    with torch.no_grad():
+        model.auto_fast_inference = False
+        xyz_m, f_m = model(data["points"], data["image"], data["xy"].clone())     # module path: cuDNN fp32
+        model.auto_fast_inference = True
+        xyz_f, f_f = model(data["points"], data["image"], data["xy"].clone())     # runner: FP16 split overflows -> TF32 split
+        assert model._f16_ok is False
+        runner = next(iter(model._runner_cache.values()))[1]
+        assert runner.f16 is False
+        xyz_2, f_2 = model(data["points"], data["image"], data["xy"].clone())     # stays on the TF32 runner
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(f_f).all()) and torch.equal(xyz_f, xyz_m)
+    scale = f_m.abs().max().item()
+    assert (f_f - f_m).abs().max().item() <= 2e-5 * scale
+    assert torch.equal(f_2, f_f)
+    # the unguarded FP16 runner really does break on this model: its output is not finite or far off
+    gemm.OverflowFlag(torch.device("cuda")).reset()
+    raw = model.make_runner(2, 16384, torch.device("cuda"), f16=True)
+    _, f_raw = raw(data["points"], data["image"], data["xy"])
+    assert raw.overflowed()
+    bad = (~torch.isfinite(f_raw)).any().item() or (f_raw - f_m).abs().max().item() > 1e-3 * scale
+    assert bad, "expected the FP16 split to fail on activations beyond 65504"
+    raw.overflow.reset()
