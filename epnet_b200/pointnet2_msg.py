@@ -212,6 +212,7 @@ class Pointnet2MSG(nn.Module):
         if entry is None or entry[0] != stamp:  # first call for this shape, or the weights changed since capture
             self._f16_ok = True
             runner = self.make_runner(key[0], key[1], key[4], image_hw=(key[2], key[3]))
+            runner.overflow.reset()  # the flag is per device and sticky: start this model's watch from a clean state
             entry = (self._state_stamp(), runner)
             self._runner_cache = {key: entry}
         xyz, feats = entry[1](pointcloud, image, xy)

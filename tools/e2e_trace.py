@@ -13,7 +13,7 @@ import bench  # noqa: E402
 
 dev = torch.device("cuda:0")
 depth = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-model = bench.build_model("ours", dev)
+model = bench.build_model(dev)
 runner = model.make_runner(2, 16384, dev, pipeline=depth)
 pinned = [{k: v.pin_memory() for k, v in b.items()} for b in bench.make_pool(4, 1000)]
 out_host, done = [None] * depth, [None] * depth

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
-model = bench.build_model("ours", dev).eval()
+model = bench.build_model(dev).eval()
 b = {k: v.to(dev) for k, v in bench.make_pool(1, 1000)[0].items()}
 rows = []
 

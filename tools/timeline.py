@@ -16,7 +16,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda:0")
-model = bench.build_model("ours", dev)
+model = bench.build_model(dev)
 runner = model.make_runner(2, 16384, dev, use_graph=False)
 pool = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_pool(2, 1000)]
 for i in range(3):

@@ -14,7 +14,7 @@ torch.backends.cudnn.allow_tf32 = tf32
 torch.backends.cuda.matmul.allow_tf32 = tf32
 torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda:0")
-model = bench.build_model(impl, dev)
+model = bench.build_model(dev)  # reference arm: bench.py --impl reference (baseline/ref_arm.py)
 model.auto_fast_inference = False
 pool = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_pool(2, 1000)]
 with torch.no_grad():

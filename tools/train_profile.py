@@ -13,7 +13,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda:0")
-model = bench.build_model(sys.argv[1] if len(sys.argv) > 1 else "ours", dev)
+model = bench.build_model(dev)
 model.train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 pool = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_pool(2, 1000)]
