@@ -95,9 +95,9 @@ def build_model(device):
     return model.to(device).eval()
 
 
-def make_pool(n_batches, first_seed):
+def make_pool(n_batches, first_seed, with_u8=False):
     from epnet_b200 import scenes
-    return [scenes.batch(first_seed + 10 * i, BATCH_PER_GPU, NPOINTS) for i in range(n_batches)]
+    return [scenes.batch(first_seed + 10 * i, BATCH_PER_GPU, NPOINTS, with_u8=with_u8 and i < 4) for i in range(n_batches)]
 
 
 # ----------------------------------------------------------------------------------------- timing
@@ -193,10 +193,12 @@ def main():
     torch.backends.cudnn.benchmark = True
     from epnet_b200 import pointnet2_cuda
     model = build_model(device)
-    host_pool = make_pool(POOL, 1000 + 1000 * rank)
-    dev_pool = [{k: v.to(device) for k, v in b.items()} for b in host_pool]
+    host_pool = make_pool(POOL, 1000 + 1000 * rank, with_u8=True)
+    dev_pool = [{k: v.to(device) for k, v in b.items() if k != "image_u8"} for b in host_pool]
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_pool[:4]]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned[0].items() if k != "image_u8")
+    h2d_bytes_u8 = sum(v.numel() * v.element_size() for k, v in pinned[0].items() if k != "image")
+    image_key = ["image"]  # which host image step_e2e uploads: the reference's fp32 tensor, or the decoded uint8 frame
 
     use_graph = not args.no_graph and args.mode == "infer"
     runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device, layout=args.layout, pipeline=args.pipeline) if use_graph else None
@@ -234,7 +236,7 @@ def main():
         if done[slot] is not None:
             done[slot].synchronize()  # the host consumes the result of the batch that used this slot `depth` steps ago
         if runner is not None and depth > 1:
-            xyz, feats = runner(hb["points"], hb["image"], hb["xy"])  # H2D from pinned memory happens on the slot's stream
+            xyz, feats = runner(hb["points"], hb[image_key[0]], hb["xy"])  # H2D from pinned memory happens on the slot's stream
             st = runner.stream_of_last_call()
         else:
             st = torch.cuda.current_stream()
@@ -291,12 +293,25 @@ def main():
         step_e2e(i)
     drain()
     ms_e2e = timed_region(step_e2e, args.steps, rank_sync, drain)
+    ms_e2e_u8 = None
+    if runner is not None and depth > 1 and args.mode == "infer":
+        # the same end-to-end step with the DECODED uint8 camera frame uploaded (2.8 MB instead of 11.8 MB per batch) and the
+        # reference's host-side normalisation + padding done by the device kernel; reported beside `e2e`,
+        # whose inputs are the reference's own fp32 tensors
+        image_key[0] = "image_u8"
+        for i in range(max(3, depth + 1)):
+            step_e2e(i)
+        drain()
+        ms_e2e_u8 = timed_region(step_e2e, args.steps, rank_sync, drain)
+        image_key[0] = "image"
     if runner is not None and runner.overflowed():
         raise RuntimeError("the FP16-split range guard fired during the timed run: results invalid (EPNET_F16_WIDE=0 selects the TF32 split)")
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host[0])
 
     from epnet_b200 import shard
     ms, ms_e2e = shard.max_over_ranks([ms, ms_e2e], device)  # slowest rank defines the job's time
+    if ms_e2e_u8 is not None:
+        (ms_e2e_u8,) = shard.max_over_ranks([ms_e2e_u8], device)
 
     scenes_total = BATCH_PER_GPU * world * args.steps
     line = {
@@ -317,6 +332,11 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if ms_e2e_u8 is not None:
+        line["e2e_uint8_image"] = {"value": round(scenes_total / (ms_e2e_u8 / 1e3), 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes_u8,
+                                   "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e_u8 / args.steps, 4),
+                                   "note": "decoded uint8 frame uploaded; normalisation, zero padding and NHWC layout on the device "
+                                           "(epnet_image_prep_u8) instead of the reference's host-side float64 preparation"}
     if args.mode == "infer" and runner is not None and depth > 1 and not args.no_latency_leg:
         # the same forward one batch at a time (graph replay, latency tile policy): what a caller that cannot keep several
         # batches in flight gets; every rank runs it (same work), rank 0 reports its own figure

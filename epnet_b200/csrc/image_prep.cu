@@ -1,0 +1,91 @@
+// Image input preparation on the device (input side).
+//
+// The reference prepares the camera image on the HOST, in float64 (lib/datasets/kitti_dataset.py:37-57: uint8 RGB -> /255 -> -mean
+// -> /std -> zero-padded (384,1280,3) canvas), collates, uploads float64 and converts/permutes on the device
+// (lib/net/train_functions.py:37: .cuda().float().permute(0,3,1,2)) -- 23.6 MB per scene over PCIe.  Here the decoded uint8 image
+// is uploaded as it is (1.4 MB per scene) and ONE kernel produces what the network consumes:
+//   * the NHWC canvas with the channel count padded to 4 that the first tcgen05 convolution reads (runner.py), and/or
+//   * the reference's own interface tensor (B,3,H,W) fp32 for the module path,
+// bit-identical to the reference's values: the 3 x 256 possible results are computed in float64 exactly as numpy does
+// ((v / 255.0 - mean) / std, IEEE division, then one rounding to fp32) into a shared-memory table.
+// The second kernel serves callers that already hold the reference's fp32 (B,3,H,W) tensor: NCHW -> NHWC4 in one pass
+// (replaces a zero-fill + strided copy of torch elementwise kernels in front of every forward).
+// Both are pure streaming kernels: HBM/L2 bandwidth bound (3 or 12 bytes in, 16 [+12] bytes out per pixel).
+#include "common.cuh"
+
+namespace epnet {
+
+__global__ void __launch_bounds__(256)
+image_prep_u8_kernel(int b, int h_in, int w_in, long long pitch_in, long long scene_in, const int *sizes, int H, int W,
+                     double m0, double m1, double m2, double s0, double s1, double s2,
+                     const uint8_t *__restrict__ src, float4 *__restrict__ nhwc4, float *__restrict__ nchw)
+{
+    __shared__ float lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        const double mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        lut[c][v] = (float)(((double)v / 255.0 - mean) / sd);  // kitti_dataset.py:46-49 in float64, train_functions.py:37 .float()
+    }
+    __syncthreads();
+    const long long total = (long long)b * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % W);
+        const long long t = p / W;
+        const int y = (int)(t % H), s = (int)(t / H);
+        const int hs = sizes ? min(__ldg(sizes + 2 * s), h_in) : h_in, ws = sizes ? min(__ldg(sizes + 2 * s + 1), w_in) : w_in;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);  // outside the decoded image the canvas is exactly zero (kitti_dataset.py:54-55)
+        if (y < hs && x < ws) {
+            const uint8_t *px = src + (size_t)s * scene_in + (size_t)y * pitch_in + (size_t)x * 3;
+            o.x = lut[0][__ldg(px)]; o.y = lut[1][__ldg(px + 1)]; o.z = lut[2][__ldg(px + 2)];
+        }
+        if (nhwc4) __stcs(nhwc4 + p, o);
+        if (nchw) {
+            float *d = nchw + ((size_t)s * 3 * H + y) * W + x;
+            d[0] = o.x; d[(size_t)H * W] = o.y; d[(size_t)2 * H * W] = o.z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+image_nchw_to_nhwc4_kernel(int b, int H, int W, const float *__restrict__ src, float4 *__restrict__ dst)
+{
+    const long long plane = (long long)H * W, total = (long long)b * plane;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const long long s = p / plane, q = p - s * plane;
+        const float *c0 = src + s * 3 * plane + q;
+        __stcs(dst + p, make_float4(__ldg(c0), __ldg(c0 + plane), __ldg(c0 + 2 * plane), 0.f));
+    }
+}
+
+}  // namespace epnet
+
+// src: b decoded images, uint8 RGB interleaved, scene s at src + s*scene_stride, row y at + y*pitch (bytes), h_in x w_in pixels
+// allocated per scene; sizes (b,2) int32 {rows, columns} actually decoded per scene on the device, or NULL = all h_in x w_in.
+// mean/std: 3 doubles each.  Outputs (either may be NULL): nhwc4 (b,H,W,4) fp32 with channel 3 = 0; nchw (b,3,H,W) fp32.
+EPNET_API int epnet_image_prep_u8(int b, int h_in, int w_in, long long pitch, long long scene_stride, const unsigned char *src,
+                                  const int *sizes, int H, int W, const double *mean, const double *std, float *nhwc4, float *nchw,
+                                  void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h_in <= 0 || w_in <= 0 || H <= 0 || W <= 0 || !src || !mean || !std || (!nhwc4 && !nchw)) return EPNET_ERR_BAD_ARG;
+    if (pitch < 3ll * w_in || scene_stride < pitch * h_in || h_in > H || w_in > W) return EPNET_ERR_BAD_ARG;
+    if (std[0] == 0.0 || std[1] == 0.0 || std[2] == 0.0 || (reinterpret_cast<uintptr_t>(nhwc4) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    const long long total = (long long)b * H * W;
+    const int blocks = (int)min((long long)kSmCount * 8, (total + 255) / 256);
+    image_prep_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, h_in, w_in, pitch, scene_stride, sizes, H, W, mean[0], mean[1], mean[2],
+                                                                  std[0], std[1], std[2], src, reinterpret_cast<float4 *>(nhwc4), nchw);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+// src (b,3,H,W) fp32 contiguous -> dst (b,H,W,4) fp32 with channel 3 = 0
+EPNET_API int epnet_image_nchw_to_nhwc4(int b, int H, int W, const float *src, float *dst, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || H <= 0 || W <= 0 || !src || !dst || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    const long long total = (long long)b * H * W;
+    const int blocks = (int)min((long long)kSmCount * 8, (total + 255) / 256);
+    image_nchw_to_nhwc4_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, H, W, src, reinterpret_cast<float4 *>(dst));
+    EPNET_RETURN_LAUNCH_STATUS();
+}

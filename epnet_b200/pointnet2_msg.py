@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import li_fusion
+from . import image_prep, li_fusion
 from . import pointnet2_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 
@@ -203,10 +203,11 @@ class Pointnet2MSG(nn.Module):
     def _state_stamp(self):
         return tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers())
 
-    def _fast_forward(self, pointcloud, image, xy):
+    def _fast_forward(self, pointcloud, image, xy, sizes=None):
         """Inference fast path behind the reference's call signature: same return values, same in-place side effect on xy."""
         c = self.config
-        key = (pointcloud.shape[0], pointcloud.shape[1], image.shape[2], image.shape[3], pointcloud.device)
+        hw = image_prep.CANVAS_HW if image.dtype == torch.uint8 else (image.shape[2], image.shape[3])
+        key = (pointcloud.shape[0], pointcloud.shape[1], hw[0], hw[1], pointcloud.device)
         stamp = self._state_stamp()
         entry = self._runner_cache.get(key)
         if entry is None or entry[0] != stamp:  # first call for this shape, or the weights changed since capture
@@ -215,7 +216,7 @@ class Pointnet2MSG(nn.Module):
             runner.overflow.reset()  # the flag is per device and sticky: start this model's watch from a clean state
             entry = (self._state_stamp(), runner)
             self._runner_cache = {key: entry}
-        xyz, feats = entry[1](pointcloud, image, xy)
+        xyz, feats = entry[1](pointcloud, image, xy, sizes)
         if self._f16_ok and entry[1].overflowed():
             # an activation left fp16's range (e.g. a checkpoint whose folded BatchNorm scales are huge): this input, and every later
             # one, runs with the TF32 operand split, whose range is fp32's
@@ -224,7 +225,7 @@ class Pointnet2MSG(nn.Module):
             runner = self.make_runner(key[0], key[1], key[4], image_hw=(key[2], key[3]), f16=False)
             entry = (stamp, runner)
             self._runner_cache = {key: entry}
-            xyz, feats = runner(pointcloud, image, xy)
+            xyz, feats = runner(pointcloud, image, xy, sizes)
         xy[:, :, 0] = xy[:, :, 0] / (c.image_size[0] - 1.0) * 2.0 - 1.0  # the reference normalises the caller's xy in place
         xy[:, :, 1] = xy[:, :, 1] / (c.image_size[1] - 1.0) * 2.0 - 1.0
         return xyz.clone(), feats.clone()  # the runner owns its output buffers
@@ -233,14 +234,19 @@ class Pointnet2MSG(nn.Module):
         self._runner_cache = {}
         return super().train(mode)
 
-    def forward(self, pointcloud: torch.Tensor, image=None, xy=None):
+    def forward(self, pointcloud: torch.Tensor, image=None, xy=None, sizes=None):
         """pointcloud (B,N,3+C), image (B,3,H,W), xy (B,N,2) pixel coordinates -> (xyz (B,N,3), features (B,128,N)).
-        Like the reference (:208-210) `xy` is normalised IN PLACE: pass a fresh copy per call."""
+        Like the reference (:208-210) `xy` is normalised IN PLACE: pass a fresh copy per call.
+        Beyond the reference: `image` may be the decoded uint8 RGB image (B,h,w,3) (+ `sizes` (B,2) int32 rows/cols per scene); it is
+        normalised and zero-padded to the 384x1280 canvas on the device (image_prep.py) instead of on the host in float64
+        (lib/datasets/kitti_dataset.py:37-57)."""
         c = self.config
         if (self.auto_fast_inference and not self.training and not torch.is_grad_enabled() and not self.reference_composition
                 and c.li_fusion and c.input_channels == 0 and image is not None and xy is not None and pointcloud.is_cuda
                 and pointcloud.shape[-1] == 3 and self._ops is pointnet2_utils.OPS):
-            return self._fast_forward(pointcloud, image, xy)
+            return self._fast_forward(pointcloud, image, xy, sizes)
+        if image is not None and image.dtype == torch.uint8:
+            image = image_prep.normalise_pad(image if image.is_cuda else image.to(pointcloud.device), sizes)
         xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz], [features]
 

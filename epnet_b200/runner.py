@@ -17,6 +17,7 @@ Only eval mode is supported here (train mode needs batch statistics: use the mod
 import torch
 import torch.nn.functional as F
 
+from . import image_prep
 from . import pointnet2_cuda as pc
 from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
 
@@ -129,7 +130,13 @@ class BackboneRunner:
         H, W = image_hw
         f32 = dict(dtype=torch.float32, device=device)
         self.points = torch.zeros(batch, npoints, 3, **f32)
-        self.image = torch.zeros(batch, 3, H, W, **f32)
+        # the graph's image input: the NHWC canvas, channels padded to 4, that the first convolution reads.  It is produced in
+        # front of the replay by one kernel from whatever the caller holds (image_prep.py): the decoded uint8 image, or the
+        # reference's fp32 (B,3,H,W) tensor.  Staging buffers for host inputs are allocated on first use.
+        self.image4 = torch.zeros(batch, H, W, 4, **f32)
+        self.image = torch.zeros(batch, 3, H, W, **f32) if layout == "cm" else None
+        self._stage_f32 = None
+        self._stage_u8 = None
         self.xy = torch.zeros(batch, npoints, 2, **f32)
         self._xy_scale = torch.tensor([c.image_size[0] - 1.0, c.image_size[1] - 1.0], **f32)
 
@@ -223,9 +230,8 @@ class BackboneRunner:
             # NHWC activations; 3x3 convolutions, transposed convolutions and the 1x1 fusion conv on the tcgen05 3xTF32 GEMM
             with torch.cuda.stream(self.s_img):
                 self.s_img.wait_event(ready)
-                H, W = self.image.shape[2], self.image.shape[3]
-                x = torch.zeros((B, H, W, 4), **f32)
-                x[..., :3] = self.image.permute(0, 2, 3, 1)
+                H, W = self.image4.shape[1], self.image4.shape[2]
+                x = self.image4
                 def run_conv(conv, inp, relu):
                     # the next convolution wants a power-of-two channel count: pad the buffer (zeros) when Cout is not one
                     cp = 4
@@ -503,17 +509,40 @@ class BackboneRunner:
         before = pc.LAUNCHES[0]
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.out = self._forward()
-        self.kernel_launches_per_replay = pc.LAUNCHES[0] - before
+        self.kernel_launches_per_replay = pc.LAUNCHES[0] - before + 1  # + the image layout/normalisation kernel in front of the replay
 
-    def _load(self, points, image, xy):
+    def _load(self, points, image, xy, sizes=None):
         self.points.copy_(points, non_blocking=True)
-        self.image.copy_(image, non_blocking=True)
         self.xy.copy_(xy, non_blocking=True)
+        if image.dtype == torch.uint8:
+            # decoded camera image (B,h,w,3) uint8, h <= H, w <= W: normalised, zero-padded and laid out on the device
+            if not image.is_cuda:
+                if self._stage_u8 is None or self._stage_u8.shape != image.shape:
+                    self._stage_u8 = torch.empty(image.shape, dtype=torch.uint8, device=self.device)
+                self._stage_u8.copy_(image, non_blocking=True)
+                image = self._stage_u8
+            if sizes is not None and not sizes.is_cuda:
+                sizes = sizes.to(self.device, non_blocking=True)
+            image_prep.normalise_pad(image, sizes, out_hw=tuple(self.image4.shape[1:3]), nhwc4=self.image4,
+                                     nchw=self.image if self.layout == "cm" else None)
+            return
+        if self.layout == "cm":
+            self.image.copy_(image, non_blocking=True)
+            return
+        if not image.is_cuda or not image.is_contiguous():
+            if self._stage_f32 is None:
+                self._stage_f32 = torch.empty(self.image4.shape[0], 3, self.image4.shape[1], self.image4.shape[2], dtype=torch.float32,
+                                              device=self.device)
+            self._stage_f32.copy_(image, non_blocking=True)
+            image = self._stage_f32
+        image_prep.nchw_to_nhwc4(image, self.image4)
 
-    def __call__(self, points, image, xy):
-        """points (B,N,3), image (B,3,H,W), xy (B,N,2) pixel coordinates (host-pinned or device; NOT modified) ->
-        (xyz (B,N,3), features (B,128,N)) in buffers owned by the runner, valid until the next call."""
-        self._load(points, image, xy)
+    def __call__(self, points, image, xy, sizes=None):
+        """points (B,N,3); image: the reference's fp32 (B,3,H,W) tensor, or the decoded uint8 RGB image (B,h,w,3) with optional
+        `sizes` (B,2) int32 {rows, cols} per scene (normalised and zero-padded on the device, image_prep.py); xy (B,N,2) pixel
+        coordinates.  Inputs may be host-pinned or on the device and are NOT modified -> (xyz (B,N,3), features (B,128,N)) in
+        buffers owned by the runner, valid until the next call."""
+        self._load(points, image, xy, sizes)
         if self.graph is None:
             with torch.no_grad():
                 out = self._forward()
@@ -563,13 +592,13 @@ class PipelinedRunner:
         self.kernel_launches_per_replay = self.runners[0].kernel_launches_per_replay
         self.calls = 0
 
-    def __call__(self, points, image, xy):
+    def __call__(self, points, image, xy, sizes=None):
         i = self.calls % len(self.runners)
         self.calls += 1
         st = self.streams[i]
         st.wait_stream(torch.cuda.current_stream(self.device))  # inputs produced on the caller's stream
         with torch.cuda.stream(st):
-            return self.runners[i](points, image, xy)
+            return self.runners[i](points, image, xy, sizes)
 
     def stream_of_last_call(self):
         return self.streams[(self.calls - 1) % len(self.runners)]

@@ -52,12 +52,31 @@ def uniform_scene(seed: int, n: int = 16384) -> torch.Tensor:
     return pts.float().contiguous()
 
 
-def batch(first_seed: int, b: int, n: int = 16384, kind: str = "lidar"):
-    """-> dict(points (B,n,3), image (B,3,384,1280), xy (B,n,2) pixel coords); scene i uses seed first_seed+i."""
+MEAN = (0.485, 0.456, 0.406)  # lib/datasets/kitti_dataset.py:24-25
+STD = (0.229, 0.224, 0.225)
+
+
+def host_image_prep(image_u8: torch.Tensor, hw=(IMG_H, IMG_W)) -> torch.Tensor:
+    """What the reference's data loader does on the host (lib/datasets/kitti_dataset.py:44-55, then the cast and permute of
+    lib/net/train_functions.py:37): uint8 (B,h,w,3) -> float64 /255, -mean, /std, zero-padded canvas -> fp32 (B,3,H,W)."""
+    im = image_u8.to(torch.float64) / 255.0
+    im = im - torch.tensor(MEAN, dtype=torch.float64)
+    im = im / torch.tensor(STD, dtype=torch.float64)
+    canvas = torch.zeros(image_u8.shape[0], hw[0], hw[1], 3, dtype=torch.float64)
+    canvas[:, :image_u8.shape[1], :image_u8.shape[2]] = im
+    return canvas.float().permute(0, 3, 1, 2).contiguous()
+
+
+def batch(first_seed: int, b: int, n: int = 16384, kind: str = "lidar", with_u8: bool = False):
+    """-> dict(points (B,n,3), image (B,3,384,1280), xy (B,n,2) pixel coords); scene i uses seed first_seed+i.
+    The image is a random decoded camera frame (uint8, 375x1242) put through the reference's host-side preparation;
+    with_u8=True also returns the frame itself as image_u8 (B,375,1242,3) for the device-side preparation."""
     make = lidar_scene if kind == "lidar" else uniform_scene
     pts = torch.stack([make(first_seed + i, n) for i in range(b)])
     g = torch.Generator().manual_seed(first_seed + 7919)
     xy = torch.stack([torch.rand(b, n, generator=g) * (VALID_W - 1), torch.rand(b, n, generator=g) * (VALID_H - 1)], dim=2)
-    image = torch.zeros(b, 3, IMG_H, IMG_W)
-    image[:, :, :VALID_H, :VALID_W] = torch.randn(b, 3, VALID_H, VALID_W, generator=g)
-    return {"points": pts, "image": image.contiguous(), "xy": xy.float().contiguous()}
+    image_u8 = torch.randint(0, 256, (b, VALID_H, VALID_W, 3), generator=g, dtype=torch.uint8)
+    out = {"points": pts, "image": host_image_prep(image_u8), "xy": xy.float().contiguous()}
+    if with_u8:
+        out["image_u8"] = image_u8.contiguous()
+    return out

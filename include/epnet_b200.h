@@ -160,6 +160,19 @@ int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int co, const f
 int epnet_gemm_overflow_read(unsigned int *host_dst, void *stream);
 int epnet_gemm_overflow_reset(void *stream);
 
+/* Image input preparation on the device.  Replaces the reference's HOST-side float64 preparation
+ * (/root/reference/lib/datasets/kitti_dataset.py:37-57: uint8 RGB -> /255 -> -mean -> /std -> zero-padded (384,1280,3) canvas) and its
+ * upload + conversion (/root/reference/lib/net/train_functions.py:37: .cuda().float().permute(0,3,1,2)).
+ * src: b decoded images, uint8 RGB interleaved; scene s starts at src + s*scene_stride, row y at + y*pitch (bytes); h_in x w_in pixels
+ * are allocated per scene; sizes (b,2) int32 {rows, columns} decoded per scene (device), or NULL = all h_in x w_in.  mean, std: 3
+ * doubles each (host).  Outputs, either may be NULL: nhwc4 (b,H,W,4) fp32, channel 3 = 0 (operand of the first convolution);
+ * nchw (b,3,H,W) fp32 (the reference's `img` tensor).  Values are bit-identical to the reference's (float64 arithmetic, one
+ * rounding to fp32); pixels outside the decoded image are exactly 0. */
+int epnet_image_prep_u8(int b, int h_in, int w_in, long long pitch, long long scene_stride, const unsigned char *src, const int *sizes,
+                        int H, int W, const double *mean, const double *std, float *nhwc4, float *nchw, void *stream);
+/* (b,3,H,W) fp32 -> (b,H,W,4) fp32, channel 3 = 0: the layout change in front of the first convolution, one pass. */
+int epnet_image_nchw_to_nhwc4(int b, int H, int W, const float *src, float *dst, void *stream);
+
 /* First shared-MLP layer of a set-abstraction scale with QueryAndGroup fused into the operand load (pointnet2_utils.py:241-264 +
  * pointnet2_modules.py:47-52): GEMM row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], 0..c) | xyz[scene, idx] -
  * new_xyz[scene, p]] is gathered straight into the tensor-core operand, the grouped tensor is never written.  feats point-major

@@ -245,3 +245,19 @@ def fps_tie_rule_bruteforce(xyz, npoint):
             last = int(tied[np.argmin(order[tied])])
             out[s, j] = last
     return out
+
+
+def image_prep(img_u8, hw=(384, 1280), mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """The reference's host-side image preparation, restated: lib/datasets/kitti_dataset.py:44-55 (float64: /255, -mean, /std,
+    zero-padded canvas) followed by the cast and permute of lib/net/train_functions.py:37 -> (B,3,H,W) float32.
+    Parity unpinned by execution: the reference function itself needs PIL and `np.float` (gone in numpy 2.x); the restatement is
+    the same four numpy statements on the same dtype.  img_u8 (B,h,w,3) uint8, or a list of (h_i,w_i,3) arrays."""
+    imgs = list(img_u8)
+    out = np.zeros([len(imgs), hw[0], hw[1], 3], dtype=np.float64)
+    for i, im in enumerate(imgs):
+        im = np.asarray(im).astype(np.float64)
+        im = im / 255.0
+        im -= np.asarray(mean)
+        im /= np.asarray(std)
+        out[i, :im.shape[0], :im.shape[1], :] = im
+    return np.ascontiguousarray(out.astype(np.float32).transpose(0, 3, 1, 2))

@@ -15,15 +15,17 @@ def test_out_of_range_weights_take_the_tf32_split():
     w = (torch.randn(256, 512, generator=g) * 1.0e5).cuda()  # |w| up to ~4e5: fp16 would be inf
     lin = gemm.PackedLinear(w, None)
     assert not lin.f16_ok
-    bn = lin.for_rows(3000)[0]
-    assert bn > 64 and not lin.wide_f16(bn)
-    y = lin(x, relu=False)
+    with gemm.tile_policy("throughput"):  # wide tiles (the latency policy would cut 3000 rows into 64-column tiles)
+        bn = lin.for_rows(3000)[0]
+        assert bn > 64 and not lin.wide_f16(bn)
+        y = lin(x, relu=False)
     want = x.double() @ w.double().t()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(y).all())
     assert (y.double() - want).abs().max().item() <= 4e-6 * want.abs().max().item()
     small = gemm.PackedLinear(w * 1e-6, None)
-    assert small.f16_ok and small.wide_f16(small.for_rows(3000)[0]) == gemm.F16_WIDE
+    with gemm.tile_policy("throughput"):
+        assert small.f16_ok and small.wide_f16(small.for_rows(3000)[0]) == gemm.F16_WIDE
 
 
 def test_overflow_flag_is_raised_by_large_outputs_and_reset():

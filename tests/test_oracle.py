@@ -145,3 +145,18 @@ def test_fps_of_an_fps_ordered_cloud_is_the_identity_prefix():
     coarse = np.stack([xyz[b][first[b]] for b in range(2)])
     again = oracle.furthest_point_sampling(coarse, 256)
     np.testing.assert_array_equal(again, np.broadcast_to(np.arange(256, dtype=np.int32), (2, 256)))
+
+
+def test_image_prep_restatement_matches_the_synthetic_loader():
+    """oracle.image_prep (numpy float64, lib/datasets/kitti_dataset.py:44-55) == scenes.host_image_prep (torch float64): the two
+    independent restatements of the reference's host-side preparation agree bit for bit, ragged sizes zero-padded."""
+    import torch
+    from epnet_b200 import scenes
+    h = scenes.batch(1000, 2, 256, with_u8=True)
+    np.testing.assert_array_equal(h["image"].numpy(), oracle.image_prep(h["image_u8"].numpy()))
+    a = np.random.RandomState(0).randint(0, 256, size=(370, 1224, 3)).astype(np.uint8)
+    out = oracle.image_prep([a])
+    assert out.shape == (1, 3, 384, 1280) and out.dtype == np.float32
+    assert np.all(out[0, :, 370:, :] == 0) and np.all(out[0, :, :, 1224:] == 0)
+    v = a[5, 7].astype(np.float64)
+    np.testing.assert_array_equal(out[0, :, 5, 7], (((v / 255.0) - np.array([0.485, 0.456, 0.406])) / np.array([0.229, 0.224, 0.225])).astype(np.float32))
