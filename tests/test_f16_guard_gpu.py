@@ -61,10 +61,10 @@ def test_backbone_falls_back_to_tf32_when_activations_leave_fp16_range():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     model = Pointnet2MSG(config=BackboneConfig()).cuda().eval()
-    with torch.no_grad():  # a "trained" BatchNorm with a tiny running variance and a large gain: folded scale ~ 9e4
+    with torch.no_grad():  # a "trained" BatchNorm with a tiny running variance and a large gain: folded scale ~ 9e5
         bn = model.Img_Block[2].bn1
         bn.running_var.fill_(1e-6)
-        bn.weight.fill_(300.0)
+        bn.weight.fill_(3000.0)
     gemm.OverflowFlag(torch.device("cuda")).reset()
     data = {k: v.cuda() for k, v in scenes.batch(1000, 2, 16384).items()}
     with torch.no_grad():

@@ -68,14 +68,15 @@ def test_backbone_from_decoded_image_equals_backbone_from_prepared_tensor(pipeli
     np.testing.assert_array_equal(host["image"].numpy(), oracle.image_prep(host["image_u8"].numpy()))  # scenes.py == oracle
     for src in ("device", "pinned"):
         b = {k: (v.cuda() if src == "device" else v.pin_memory()) for k, v in host.items()}
-        xyz_a, f_a = [t.clone() for t in runner(b["points"], b["image"], b["xy"])]
-        if pipeline > 1:
-            runner.join()
-        torch.cuda.synchronize()
-        xyz_b, f_b = [t.clone() for t in runner(b["points"], b["image_u8"], b["xy"])]
-        if pipeline > 1:
-            runner.join()
-        torch.cuda.synchronize()
+        def run(image):  # a pipelined slot runs on its own stream: wait for it before reading the runner-owned result
+            out = runner(b["points"], image, b["xy"])
+            if pipeline > 1:
+                runner.join()
+            torch.cuda.synchronize()
+            return [t.clone() for t in out]
+
+        xyz_a, f_a = run(b["image"])
+        xyz_b, f_b = run(b["image_u8"])
         assert torch.equal(xyz_a, xyz_b) and torch.equal(f_a, f_b)  # same canvas bit for bit -> same features bit for bit
     # the module path takes the decoded image too
     model.auto_fast_inference = False

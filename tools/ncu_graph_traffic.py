@@ -36,7 +36,7 @@ def main(src, dst, replays=1):
         except (KeyError, ValueError):
             continue
         unit = r.get("Metric Unit", "")
-        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0}.get(unit, 1.0)
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(unit, 1.0)
         per[i][r["Metric Name"]] = v * scale
     fam = defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "seconds": 0.0})
     kernels = defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "seconds": 0.0})
