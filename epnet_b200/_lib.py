@@ -52,6 +52,13 @@ SIGNATURES = {
     "epnet_nms_rotated": [_c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int] + [_c_void_p] * 4,
     "epnet_nms_normal": [_c_int, _c_int, _c_void_p, _c_void_p, _c_float, _c_int] + [_c_void_p] * 4,
     "epnet_gemm_tf32x3": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_conv3x3_planes_tma": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p,
+                                 _c_int, _c_void_p],
+    "epnet_gemm_planes_tma": [_c_int] * 3 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p,
+                              _c_void_p, _c_int, _c_void_p],
+    "epnet_deconv_planes_tma": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
+    "epnet_conv3x3_nhwc_tf32x3_planes": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,
+                                         _c_void_p],
     "epnet_image_prep_u8": [_c_int] * 3 + [_c_ll, _c_ll, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "epnet_image_nchw_to_nhwc4": [_c_int] * 3 + [_c_void_p, _c_void_p, _c_void_p],
     "epnet_gemm_overflow_read": [_c_void_p, _c_void_p],

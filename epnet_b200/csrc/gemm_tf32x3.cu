@@ -22,6 +22,8 @@
 //     ReLU, 128-bit stores; with pool > 1 the max over `pool` consecutive rows (the nsample axis of a grouped
 //     tensor, F.max_pool2d in pointnet2_modules.py:59-61) is taken across lanes with redux.sync before storing.
 #include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
 namespace epnet {
@@ -122,6 +124,15 @@ struct GemmArgs {
     int kcopy;             // columns of a row that are read from x (== K unless grouped)
     int f16;               // weights are packed as FP16 planes (k-blocks of 64): wide-tile FP16-split kernel
     float corr_scale;      // the correction accumulator is multiplied by this in the epilogue (1 for the TF32 split, 2^-11 for FP16)
+    // Optional second output of the plain-rows epilogue: the result already split into the two FP16 planes the next FP16-split
+    // layer consumes (h1 = fp16(v), h2 = fp16((v - h1) * 2^11)), rows ldh halfs apart.  A consumer that reads the planes with TMA
+    // (gemm_f16x3_tma_kernel) does no conversion work at all: every activation is split ONCE, by its producer, instead of once per
+    // tap and column tile by its consumers.  y may then be NULL (planes only).
+    __half *yh1, *yh2;
+    int ldh;
+    // gemm_f16x3_tma_kernel, convolution mode: a CTA's 128 rows are a th x tw patch of output pixels (tw * th == 128), patches in
+    // raster order over (image, patch row, patch column); 0 = rows are linear
+    int tw, th, tiles_x, tiles_y;
 };
 
 // 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
@@ -256,6 +267,12 @@ struct RowSource {
     }
 };
 
+__device__ __forceinline__ void split_f16(float x, __half &h1, __half &h2)
+{
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(h1)), 2048.0f));
+}
+
 // Range guard of the FP16 operand split: gemm_f16x3_kernel needs |x| < 65504.  Every value such a kernel can read is bounded by
 // a value some GEMM epilogue of this file wrote (activations of the previous layer; interpolation, bilinear gathering, max-pooling
 // and the sigmoid attention scale are convex combinations or contractions of them), so every epilogue raises this per-device flag
@@ -267,11 +284,11 @@ constexpr float kF16Guard = 6.0e4f;
 // Accumulator -> global memory: main + correction, bias, ReLU, then plain rows / pooled rows / the transposed convolution's
 // patch scatter.  Called by the four warps whose warp index selects the TMEM lane quarter (thread = lane = tile row).
 __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_acc, uint32_t corr_off, int warp, int lane, int row0,
-                                              int ntile, const float *bias_s, int c_first = 0, int c_step = 32)
+                                              int ntile, const float *bias_s, int c_first = 0, int c_step = 32, int row_override = -1)
 {
     const int BN = a.BN;
     const int r = warp * 32 + lane;  // TMEM lane == tile row
-    const int row = row0 + r;
+    const int row = row_override >= 0 ? row_override : row0 + r;  // override: the caller maps tile rows to output rows itself
     const int pool = a.pool;
     float amax = 0.f;
     for (int c0 = c_first; c0 < BN; c0 += c_step) {
@@ -313,7 +330,26 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
                 }
             }
         } else if (pool == 1) {
-            if (row < a.L) {
+            if (row < a.L && a.yh1) {  // FP16 planes for the next layer (n0, ncols, ldh multiples of 8: checked by the host entry)
+                __half *d1 = a.yh1 + (size_t)row * a.ldh + n0, *d2 = a.yh2 + (size_t)row * a.ldh + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncols) {
+                        uint32_t q1[4], q2[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __half a1, a2, b1, b2;
+                            split_f16(__uint_as_float(v[j + 2 * e]), a1, a2);
+                            split_f16(__uint_as_float(v[j + 2 * e + 1]), b1, b2);
+                            q1[e] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
+                            q2[e] = (uint32_t)__half_as_ushort(a2) | ((uint32_t)__half_as_ushort(b2) << 16);
+                        }
+                        *reinterpret_cast<uint4 *>(d1 + j) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+                        *reinterpret_cast<uint4 *>(d2 + j) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+                    }
+                }
+            }
+            if (row < a.L && a.y) {
                 float *dst = a.y + (size_t)row * a.ldy + n0;
                 if (n0 + ncols <= a.N && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
 #pragma unroll
@@ -536,12 +572,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
-}
-
-__device__ __forceinline__ void split_f16(float x, __half &h1, __half &h2)
-{
-    h1 = __float2half_rn(x);
-    h2 = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(h1)), 2048.0f));
 }
 
 __global__ void __launch_bounds__(kHfThreads, 1)
@@ -934,6 +964,179 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// FP16-split GEMM / 3x3 convolution whose A operand arrives ALREADY SPLIT (two FP16 planes written by the producing layer's
+// epilogue, GemmArgs::yh1/yh2) and is moved by TMA TENSOR loads (cp.async.bulk.tensor, SASS UTMALDG) straight into the swizzled
+// shared-memory image the MMA reads.  Compared with gemm_f16x3_kernel there are no producer warps at all: nothing is converted,
+// nothing is addressed per thread -- one elected thread issues two tensor copies (planes h1, h2) and one bulk copy (weights) per
+// k-block; image borders (padding 1) and ragged tile edges are the TMA unit's out-of-bounds zero fill; stride-2 convolutions use
+// the tensor map's traversal stride.  An implicit-GEMM convolution re-reads every input pixel for 9 taps and every column tile;
+// with SIMT producers it also re-CONVERTED it each time (measured: the N <= 128 convolutions were bound by that work).
+//
+// Convolution mode: x planes are NHWC FP16 images (B, H, W, ldx >= Cin), Cin % 64 == 0; a k-block is one tap x 64 channels:
+// box {64 ch, tw px, th px, 1 image} at coordinates {c0, ox0*stride + kx - 1, oy0*stride + ky - 1, b} -> 128 rows of 128 bytes,
+// row r = (y_local * tw + x_local), SWIZZLE_128B -- exactly the K-major UMMA layout.  Plain mode: planes are (L, ldx) rows, box
+// {64, 128}.  6 warps: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer, 5 TMA producer.  One CTA per SM.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kTmaThreads = 192;
+
+__device__ __forceinline__ void tma_load_4d(void *dst_smem, const void *tmap, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+struct TmaMaps {
+    alignas(64) unsigned char h1[128];  // CUtensorMap of plane h1
+    alignas(64) unsigned char h2[128];  // CUtensorMap of plane h2
+};
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
+{
+    extern __shared__ __align__(1024) uint8_t gm_smem[];
+    __shared__ __align__(8) uint64_t full[kGmMaxStages], empty[kGmMaxStages], accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float bias_s[256 + 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntile = blockIdx.y;
+    const int BN = a.BN;
+    const uint32_t a_bytes = kGmBM * 128;
+    const uint32_t b_bytes = (uint32_t)BN * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
+    const uint32_t BNP = (uint32_t)((BN + 31) & ~31);
+    const uint32_t corr_off = BN <= 128 ? (uint32_t)BN : BNP;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2 * BNP) tmem_cols <<= 1;
+
+    // this CTA's 128 rows: a th x tw patch of output pixels (convolution) or rows [row0, row0 + 128)
+    int img = 0, oy0 = 0, ox0 = 0;
+    if (a.tw) {
+        const int per_img = a.tiles_x * a.tiles_y;
+        img = blockIdx.x / per_img;
+        const int t = blockIdx.x - img * per_img;
+        oy0 = (t / a.tiles_x) * a.th;
+        ox0 = (t - (t / a.tiles_x) * a.tiles_x) * a.tw;
+    }
+    const int row0 = blockIdx.x * kGmBM;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 5 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(maps.h1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(maps.h2)) : "memory");
+    }
+    for (int j = tid; j < 256 + 32; j += kTmaThreads) {
+        const int n = ntile * BN + j;
+        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp < 4) {
+        // ===================== epilogue =====================
+        int row = row0 + warp * 32 + lane;
+        if (a.tw) {
+            const int r = warp * 32 + lane;
+            const int oy = oy0 + r / a.tw, ox = ox0 + (r - (r / a.tw) * a.tw);
+            row = (oy < a.Ho && ox < a.Wo) ? (img * a.Ho + oy) * a.Wo + ox : a.L;  // a.L: outside the image, nothing is stored
+        }
+        mbar_wait(&accum_bar, 0u);
+        tc_fence_after();
+        gemm_epilogue(a, tmem_acc, corr_off, warp, lane, row0, ntile, bias_s, 0, 32, row);
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== MMA issuer (one thread): same MMA sequence as gemm_f16x3_kernel =====================
+        if (lane == 0) {
+            const bool fused_b = BN <= 128;
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t d_a1 = umma_desc_k_sw128(base), d_a2 = umma_desc_k_sw128(base + a_bytes);
+                const uint64_t d_b1 = umma_desc_k_sw128(base + 2 * a_bytes), d_b2 = umma_desc_k_sw128(base + 2 * a_bytes + b_bytes);
+#pragma unroll
+                for (int ks = 0; ks < kHfBK / 16; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);
+                    if (fused_b) {
+                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc2, (kb | ks) ? 1u : 0u);
+                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, 1u);
+                    } else {
+                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                        umma_f16(tmem_acc + corr_off, d_a1 + adv, d_b2 + adv, idesc, 1u);
+                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(&accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ===================== TMA producer (one thread): planes by tensor copies, weights by a bulk copy =====================
+        if (lane == 0) {
+            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
+            const int kpc = a.conv ? (1 << a.cin_shift) / kHfBK : 1;  // k-blocks per tap
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[s], 2 * a_bytes + 2 * b_bytes);
+                uint8_t *st = smem + (size_t)s * stage_bytes;
+                if (a.conv) {
+                    const int tap = kb / kpc, c0 = (kb - tap * kpc) * kHfBK;
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    const int cx = ox0 * a.stride + kx - 1, cy = oy0 * a.stride + ky - 1;
+                    tma_load_4d(st, maps.h1, &full[s], c0, cx, cy, img);
+                    tma_load_4d(st + a_bytes, maps.h2, &full[s], c0, cx, cy, img);
+                } else {
+                    tma_load_2d(st, maps.h1, &full[s], kb * kHfBK, row0);
+                    tma_load_2d(st + a_bytes, maps.h2, &full[s], kb * kHfBK, row0);
+                }
+                bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full[s]);
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    }
+}
+
 }  // namespace epnet
 
 namespace epnet {
@@ -1070,12 +1273,14 @@ EPNET_API int epnet_gemm_tf32x3_cm(int L, int K, int N, int pts, const float *x,
 // 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM on an NHWC image: x (B, H, W, Cin) with Cin a power of two
 // >= 4; wpack packs W reordered to (Cout, ky, kx, Cin) (K = 9*Cin); y (B*Ho*Wo, ldy) = NHWC output, bias/ReLU optional.
 static int conv_entry(int f16, int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
-                      const float *bias, int relu, float *y, int ldy, void *stream)
+                      const float *bias, int relu, float *y, int ldy, void *stream, void *yh1 = nullptr, void *yh2 = nullptr, int ldh = 0)
 {
     using namespace epnet;
-    if (b < 0 || h <= 0 || w <= 0 || cin < 4 || (cin & (cin - 1)) != 0 || cout <= 0 || (stride != 1 && stride != 2) || !x || !wpack || !y)
+    if (b < 0 || h <= 0 || w <= 0 || cin < 4 || (cin & (cin - 1)) != 0 || cout <= 0 || (stride != 1 && stride != 2) || !x || !wpack || (!y && !yh1))
         return EPNET_ERR_BAD_ARG;
-    if (BN < 16 || BN > 256 || (BN % 16) != 0 || ldy < cout || h >= 32768 || w >= 32768) return EPNET_ERR_BAD_ARG;
+    if (yh1 && (!yh2 || ((reinterpret_cast<uintptr_t>(yh1) | reinterpret_cast<uintptr_t>(yh2)) & 15) != 0 || ldh < cout || (ldh % 8) != 0 || (cout % 8) != 0))
+        return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || (y && ldy < cout) || h >= 32768 || w >= 32768) return EPNET_ERR_BAD_ARG;
     if (((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(x)) & 15) != 0) return EPNET_ERR_BAD_ARG;
     if (b == 0) return EPNET_OK;
     GemmArgs a = {};
@@ -1088,7 +1293,16 @@ static int conv_entry(int f16, int b, int h, int w, int cin, int cout, int strid
     if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
     a.L = (int)rows; a.K = 9 * cin; a.N = cout; a.ldx = cin; a.ldy = ldy; a.BN = BN;
     a.relu = relu; a.pool = 1; a.x_vec_ok = 1; a.f16 = f16;
+    a.yh1 = reinterpret_cast<__half *>(yh1); a.yh2 = reinterpret_cast<__half *>(yh2); a.ldh = ldh;
     return gemm_launch(a, (cudaStream_t)stream);
+}
+// The TF32-split convolution (fp32 NHWC input) that ALSO writes its result as the FP16 planes the next layer reads with TMA
+// (epnet_conv3x3_planes_tma); y may be NULL.  Used for the first convolution of the image stream (Cin = 3 -> 4).
+EPNET_API int epnet_conv3x3_nhwc_tf32x3_planes(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                                               const float *bias, int relu, float *y, int ldy, void *yh1, void *yh2, int ldh, void *stream)
+{
+    if (!yh1) return EPNET_ERR_BAD_ARG;
+    return conv_entry(0, b, h, w, cin, cout, stride, x, wpack, BN, bias, relu, y, ldy, stream, yh1, yh2, ldh);
 }
 EPNET_API int epnet_conv3x3_nhwc_tf32x3(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
                                         const float *bias, int relu, float *y, int ldy, void *stream)
@@ -1133,6 +1347,151 @@ EPNET_API int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int c
                                       const float *bias, int relu, float *out, int ldo, void *stream)
 {
     return deconv_entry(1, b, h, w, cin, k, co, x, ldx, wpack, BN, bias, relu, out, ldo, stream);
+}
+
+
+// ---- gemm_f16x3_tma_kernel: host side ---------------------------------------------------------------------------------------
+namespace epnet {
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library does not link libcuda
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+constexpr int kTmaTileW = 16, kTmaTileH = 8;  // output pixels per CTA tile: 16 x 8 = 128 GEMM rows
+
+// planes xh1/xh2: convolution mode (a.conv) NHWC FP16 images (b, H, W, ldx), else (L, ldx) rows
+static int gemm_launch_tma(GemmArgs &a, const void *xh1, const void *xh2, int ldx, int batch, cudaStream_t st)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "TmaMaps holds raw CUtensorMap bytes");
+    PFN_cuTensorMapEncodeTiled encode = tensor_map_encoder();
+    if (!encode) return (int)cudaErrorNotSupported;
+    a.n_kblocks = (a.K + kHfBK - 1) / kHfBK;
+    a.kcopy = a.K;
+    a.f16 = 1;
+    a.corr_scale = 1.0f / 2048.0f;
+    const int n_tiles = (a.N + a.BN - 1) / a.BN;
+    TmaMaps maps;
+    const void *planes[2] = {xh1, xh2};
+    for (int i = 0; i < 2; ++i) {
+        CUtensorMap *m = reinterpret_cast<CUtensorMap *>(i == 0 ? maps.h1 : maps.h2);
+        CUresult r;
+        if (a.conv) {
+            const cuuint64_t gdim[4] = {(cuuint64_t)(1 << a.cin_shift), (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)batch};
+            const cuuint64_t gstr[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)a.W * ldx * 2, (cuuint64_t)a.H * a.W * ldx * 2};
+            const cuuint32_t box[4] = {(cuuint32_t)kHfBK, (cuuint32_t)(kTmaTileW * a.stride), (cuuint32_t)(kTmaTileH * a.stride), 1u};
+            const cuuint32_t estr[4] = {1u, (cuuint32_t)a.stride, (cuuint32_t)a.stride, 1u};
+            r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(planes[i]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.L};
+            const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
+            const cuuint32_t box[2] = {(cuuint32_t)kHfBK, (cuuint32_t)kGmBM};
+            const cuuint32_t estr[2] = {1u, 1u};
+            r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(planes[i]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) return EPNET_ERR_BAD_ARG;
+    }
+    dim3 grid;
+    if (a.conv) {
+        a.tw = kTmaTileW; a.th = kTmaTileH;
+        a.tiles_x = (a.Wo + kTmaTileW - 1) / kTmaTileW;
+        a.tiles_y = (a.Ho + kTmaTileH - 1) / kTmaTileH;
+        grid = dim3((unsigned)(batch * a.tiles_x * a.tiles_y), (unsigned)n_tiles);
+    } else {
+        grid = dim3((unsigned)((a.L + kGmBM - 1) / kGmBM), (unsigned)n_tiles);
+    }
+    const size_t sb = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
+    int st_ = (int)((200 * 1024) / sb);
+    if (st_ > kGmMaxStages) st_ = kGmMaxStages;
+    if (st_ > a.n_kblocks) st_ = a.n_kblocks;
+    if (st_ < 1) st_ = 1;
+    a.stages = st_;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)gemm_f16x3_tma_kernel);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute((const void *)gemm_f16x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return (int)e;
+    gemm_f16x3_tma_kernel<<<grid, kTmaThreads, sb * st_ + 1024, st>>>(a, maps);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+static bool planes_ok(const void *h1, const void *h2, int ld)
+{
+    return h1 && h2 && ((reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(h2)) & 15) == 0 && ld > 0 && (ld % 8) == 0;
+}
+}  // namespace epnet
+
+// 3x3 convolution, padding 1, stride 1 or 2, whose input is the pair of FP16 planes a previous layer's epilogue wrote
+// (xh1, xh2: NHWC (b, h, w, ldx) halfs, cin % 64 == 0 channels read).  wpack = FP16 planes of W reordered to (Cout, ky, kx, Cin) in
+// k-blocks of 64 (epnet_b200/gemm.py).  Outputs: y (b*Ho*Wo, ldy) fp32 NHWC and/or the FP16 planes yh1/yh2 (b*Ho*Wo, ldh) for the next
+// layer; either may be NULL, not both.
+EPNET_API int epnet_conv3x3_planes_tma(int b, int h, int w, int cin, int cout, int stride, const void *xh1, const void *xh2, int ldx,
+                                       const float *wpack, int BN, const float *bias, int relu, float *y, int ldy, void *yh1, void *yh2,
+                                       int ldh, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h <= 0 || w <= 0 || cin < 64 || (cin & (cin - 1)) != 0 || cout <= 0 || (stride != 1 && stride != 2) || !wpack) return EPNET_ERR_BAD_ARG;
+    if (!planes_ok(xh1, xh2, ldx) || ldx < cin || BN < 16 || BN > 256 || (BN % 16) != 0 || h >= 32768 || w >= 32768) return EPNET_ERR_BAD_ARG;
+    if ((!y && !yh1) || (y && ldy < cout) || (yh1 && (!planes_ok(yh1, yh2, ldh) || ldh < cout || (cout % 8) != 0))) return EPNET_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.wpack = wpack; a.bias = bias; a.y = y;
+    a.yh1 = reinterpret_cast<__half *>(yh1); a.yh2 = reinterpret_cast<__half *>(yh2); a.ldh = ldh;
+    a.conv = 1; a.H = h; a.W = w; a.stride = stride;
+    a.Ho = (h + 2 - 3) / stride + 1; a.Wo = (w + 2 - 3) / stride + 1;
+    while ((1 << a.cin_shift) < cin) ++a.cin_shift;
+    const long long rows = (long long)b * a.Ho * a.Wo;
+    if (rows >= (1ll << 31)) return EPNET_ERR_BAD_ARG;
+    a.L = (int)rows; a.K = 9 * cin; a.N = cout; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
+    a.relu = relu; a.pool = 1;
+    return gemm_launch_tma(a, xh1, xh2, ldx, b, (cudaStream_t)stream);
+}
+
+// Y = act(X W^T + b) with X given as FP16 planes (L, ldx) (K read, ldx % 8 == 0): plain rows out (y fp32 and/or planes), optional
+// max-pool over `pool` consecutive rows (fp32 output only).
+EPNET_API int epnet_gemm_planes_tma(int L, int K, int N, const void *xh1, const void *xh2, int ldx, const float *wpack, int BN,
+                                    const float *bias, int relu, int pool, float *y, int ldy, void *yh1, void *yh2, int ldh, void *stream)
+{
+    using namespace epnet;
+    if (L < 0 || K <= 0 || N <= 0 || !wpack || !planes_ok(xh1, xh2, ldx) || ldx < K) return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || (reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (pool < 1 || pool > 32 || (32 % pool) != 0 || (L % pool) != 0) return EPNET_ERR_BAD_ARG;
+    if ((!y && !yh1) || (y && ldy < N) || (yh1 && (pool != 1 || !planes_ok(yh1, yh2, ldh) || ldh < N || (N % 8) != 0))) return EPNET_ERR_BAD_ARG;
+    if (L == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.wpack = wpack; a.bias = bias; a.y = y;
+    a.yh1 = reinterpret_cast<__half *>(yh1); a.yh2 = reinterpret_cast<__half *>(yh2); a.ldh = ldh;
+    a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN; a.relu = relu; a.pool = pool;
+    return gemm_launch_tma(a, xh1, xh2, ldx, 1, (cudaStream_t)stream);
+}
+
+// Transposed convolution (kernel == stride == k) whose input map is given as FP16 planes (b*h*w, ldx): see epnet_deconv_nhwc_tf32x3.
+EPNET_API int epnet_deconv_planes_tma(int b, int h, int w, int cin, int k, int co, const void *xh1, const void *xh2, int ldx,
+                                      const float *wpack, int BN, const float *bias, int relu, float *out, int ldo, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || h <= 0 || w <= 0 || cin <= 0 || k <= 0 || co <= 0 || (co % 4) != 0 || !wpack || !out || !planes_ok(xh1, xh2, ldx) || ldx < cin || ldo < co)
+        return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 256 || (BN % 16) != 0 || (ldo % 4) != 0) return EPNET_ERR_BAD_ARG;
+    if (((reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    const long long rows = (long long)b * h * w, cols = (long long)k * k * co;
+    if (rows >= (1ll << 31) || cols >= (1ll << 24)) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.wpack = wpack; a.bias = bias; a.y = out;
+    a.L = (int)rows; a.K = cin; a.N = (int)cols; a.ldx = ldx; a.ldy = ldo; a.BN = BN;
+    a.relu = relu; a.pool = 1; a.H = h; a.W = w; a.dk = k; a.dco = co;
+    return gemm_launch_tma(a, xh1, xh2, ldx, 1, (cudaStream_t)stream);
 }
 
 // FP16-split range guard (see g_gemm_overflow): asynchronous read of the per-device flag into host memory (pinned for a truly

@@ -88,6 +88,38 @@ def choose_bn(n, rows=None):
     return bn
 
 
+class Planes:
+    """An activation stored as the two FP16 planes of the FP16 split (x = h1 + 2^-11 h2), written by the producing layer's epilogue and
+    read by the consuming layer with TMA (csrc/gemm_tf32x3.cu, gemm_f16x3_tma_kernel).  h1, h2: (..., C) float16, last stride 1."""
+
+    def __init__(self, h1, h2):
+        assert h1.dtype == torch.float16 and h2.dtype == torch.float16 and h1.shape == h2.shape and h1.stride() == h2.stride()
+        self.h1, self.h2 = h1, h2
+
+    @classmethod
+    def empty(cls, shape, device):
+        buf = torch.empty((2,) + tuple(shape), dtype=torch.float16, device=device)
+        return cls(buf[0], buf[1])
+
+    @property
+    def shape(self):
+        return self.h1.shape
+
+    def float(self):
+        """the fp32 value the planes represent (tests)"""
+        return self.h1.float() + self.h2.float() / 2048.0
+
+
+def tma_bn(n, rows):
+    """column tile of the TMA-fed FP16-split kernel: the whole layer up to 256 columns; 128 when 256-column tiles would leave most SMs idle"""
+    if n <= 256:
+        return (n + 15) // 16 * 16
+    bn = 256
+    if ((rows + 127) // 128) * ((n + 255) // 256) < 100 and n % 128 == 0:
+        bn = 128
+    return bn
+
+
 class PackedLinear:
     """W (N,K) fp32 [+ bias (N)] -> the shared-memory image the MMA consumes.
 
@@ -163,6 +195,21 @@ class PackedLinear:
             # TF32 tiles (235 -> 218 us, 133 -> 110 us); short-K layers of that width stay on the persistent narrow-tile kernel
             bn = (self.N + 15) // 16 * 16
         return bn, self._pack(bn)
+
+    def from_planes(self, x, relu=True, pool=1, out=None, planes_out=False, f32_out=True):
+        """x: Planes (L, >=K) -> (L / pool, N) fp32 and/or Planes: the TMA-fed FP16-split kernel (weights must be inside fp16's range)"""
+        assert isinstance(x, Planes) and self.f16_ok and x.h1.dim() == 2 and x.h1.stride(-1) == 1
+        L, ldx = x.shape[0], x.h1.stride(0)
+        dev = x.h1.device
+        if out is None and f32_out:
+            out = torch.empty((L // pool, self.N), dtype=torch.float32, device=dev)
+        planes = Planes.empty((L, self.N), dev) if planes_out else None
+        bn = tma_bn(self.N, L)
+        pc._call("gemm_planes_tma", LIB.epnet_gemm_planes_tma, x.h1, L, self.K, self.N, x.h1.data_ptr(), x.h2.data_ptr(), ldx,
+                 self._pack16(bn).data_ptr(), bn, None if self.bias is None else self.bias.data_ptr(), int(bool(relu)), pool,
+                 None if out is None else out.data_ptr(), 0 if out is None else out.stride(0),
+                 None if planes is None else planes.h1.data_ptr(), None if planes is None else planes.h2.data_ptr(), self.N)
+        return (out, planes) if planes_out else out
 
     def __call__(self, x, relu=True, pool=1, out=None, out_cm=None):
         """x (..., K) point-major rows (last dim contiguous) -> (rows / pool, N); with out_cm (B, N, pts) contiguous the result
@@ -256,15 +303,44 @@ class PackedConv3x3:
         self.lin = PackedLinear(wp.reshape(cout, 9 * cin_p), bias)
         self.cin, self.cin_p, self.cout, self.stride = cin, cin_p, cout, stride
 
-    def __call__(self, x, relu=False, out=None):
-        """x (B, H, W, cin_p) NHWC contiguous -> (B, Ho, Wo, Cout)"""
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin_p
-        B, H, W, _ = x.shape
-        Ho, Wo = (H - 1) // self.stride + 1, (W - 1) // self.stride + 1
-        if out is None:
-            out = torch.empty((B, Ho, Wo, self.cout), dtype=torch.float32, device=x.device)
-        assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
+    def planes_capable(self):
+        """can this layer read its input as FP16 planes through TMA (k-blocks of one tap x 64 channels; weights inside fp16's range)?"""
+        return F16_WIDE and self.lin.f16_ok and self.cin_p % 64 == 0
+
+    def __call__(self, x, relu=False, out=None, planes_out=False, f32_out=True):
+        """x (B, H, W, cin_p) NHWC contiguous fp32, or Planes of that shape -> (B, Ho, Wo, Cout) fp32.
+        planes_out=True: also return the result as Planes for a following planes-fed layer -> (out, planes); with f32_out=False
+        only the planes are written -> (None, planes)."""
         lin = self.lin
+        if isinstance(x, Planes):
+            assert self.planes_capable() and x.h1.is_cuda and x.shape[-1] >= self.cin_p and x.h1.stride(-1) == 1
+            B, H, W, _ = x.shape
+            ldx = x.h1.stride(-2)
+            assert x.h1.stride(-3) == W * ldx and x.h1.stride(0) == H * W * ldx
+        else:
+            assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin_p
+            B, H, W, _ = x.shape
+        Ho, Wo = (H - 1) // self.stride + 1, (W - 1) // self.stride + 1
+        dev = x.h1.device if isinstance(x, Planes) else x.device
+        if out is None and f32_out:
+            out = torch.empty((B, Ho, Wo, self.cout), dtype=torch.float32, device=dev)
+        planes = Planes.empty((B, Ho, Wo, self.cout), dev) if planes_out else None
+        if out is not None:
+            assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
+        ph1 = None if planes is None else planes.h1.data_ptr()
+        ph2 = None if planes is None else planes.h2.data_ptr()
+        if isinstance(x, Planes):
+            bn = tma_bn(self.cout, B * Ho * Wo)
+            pc._call("conv3x3_planes_tma", LIB.epnet_conv3x3_planes_tma, x.h1, B, H, W, self.cin_p, self.cout, self.stride, x.h1.data_ptr(),
+                     x.h2.data_ptr(), ldx, lin._pack16(bn).data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)),
+                     None if out is None else out.data_ptr(), 0 if out is None else out.stride(-2), ph1, ph2, self.cout)
+            return (out, planes) if planes_out else out
+        if planes_out:  # fp32 input, planes (and optionally fp32) out: the TF32-split kernels
+            bn = choose_bn(self.cout, B * Ho * Wo)
+            pc._call("conv3x3_nhwc_tf32x3", LIB.epnet_conv3x3_nhwc_tf32x3_planes, x, B, H, W, self.cin_p, self.cout, self.stride, x.data_ptr(),
+                     lin._pack(bn).data_ptr(), bn, None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)),
+                     None if out is None else out.data_ptr(), 0 if out is None else out.stride(-2), ph1, ph2, self.cout)
+            return out, planes
         bn, wpack = lin.for_rows(B * Ho * Wo)
         fn = LIB.epnet_conv3x3_nhwc_tf32x3
         if lin.wide_f16(bn):

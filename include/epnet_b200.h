@@ -153,6 +153,25 @@ int epnet_conv3x3_nhwc_f16x3(int b, int h, int w, int cin, int cout, int stride,
 int epnet_deconv_nhwc_f16x3(int b, int h, int w, int cin, int k, int co, const float *x, int ldx, const float *wpack, int BN,
                             const float *bias, int relu, float *out, int ldo, void *stream);
 
+/* FP16-split layers whose A operand arrives ALREADY SPLIT into two FP16 planes (x = h1 + 2^-11 h2, written by the producing layer's
+ * epilogue through the yh1/yh2 outputs below) and is moved by TMA tensor loads (cp.async.bulk.tensor) -- no conversion work, no
+ * per-thread addressing; image borders and ragged tiles are the TMA unit's zero fill, stride 2 its traversal stride.  Same arithmetic
+ * as the *_f16x3 entry points (same split, same MMA sequence).  Replace the same reference layers: the image stream's 3x3
+ * convolutions (/root/reference/lib/net/pointnet2_msg.py:17-33), Conv2d(1x1)+BN+ReLU units (pytorch_utils.py:20-32), transposed
+ * convolutions (pointnet2_msg.py:163-168).  Planes: FP16, 16-byte aligned, row/pixel stride (ldx, ldh) a multiple of 8 halfs.
+ * Outputs: y fp32 and/or planes yh1/yh2 (either may be NULL, not both). */
+int epnet_conv3x3_planes_tma(int b, int h, int w, int cin, int cout, int stride, const void *xh1, const void *xh2, int ldx,
+                             const float *wpack, int BN, const float *bias, int relu, float *y, int ldy, void *yh1, void *yh2, int ldh,
+                             void *stream);
+int epnet_gemm_planes_tma(int L, int K, int N, const void *xh1, const void *xh2, int ldx, const float *wpack, int BN, const float *bias,
+                          int relu, int pool, float *y, int ldy, void *yh1, void *yh2, int ldh, void *stream);
+int epnet_deconv_planes_tma(int b, int h, int w, int cin, int k, int co, const void *xh1, const void *xh2, int ldx, const float *wpack,
+                            int BN, const float *bias, int relu, float *out, int ldo, void *stream);
+/* epnet_conv3x3_nhwc_tf32x3 (fp32 NHWC input, TF32 split) that also writes its result as FP16 planes for a following *_planes_tma layer;
+ * y may be NULL. */
+int epnet_conv3x3_nhwc_tf32x3_planes(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
+                                     const float *bias, int relu, float *y, int ldy, void *yh1, void *yh2, int ldh, void *stream);
+
 /* Range guard of the FP16 operand split (no reference counterpart: pytorch_utils.py:20-32 computes in fp32).  Every GEMM
  * epilogue of this library raises a per-device flag when it writes a magnitude above 6e4 or a non-finite value -- i.e. whenever
  * a following FP16-split layer could overflow.  _read copies the flag (0/1) to host memory asynchronously on `stream` (pinned
