@@ -209,7 +209,8 @@ def measure(model, runner, dev_pool, device, world, ms_per_step=None, batches_in
     for (name, ints), (tot, cnt) in agg.items():
         # plain, implicit-convolution and transposed-convolution launches are the same device code: gemm_tf32x3_kernel
         # (tiles wider than 64 columns) or gemm_tf32x3_ts_kernel (A operand through TMEM, tiles of <= 64 columns)
-        family = ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3", "gemm_tf32x3_grouped", "gemm_tf32x3_cm")
+        family = ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3", "gemm_tf32x3_grouped", "gemm_tf32x3_cm", "conv3x3_planes_tma",
+                  "gemm_planes_tma", "deconv_planes_tma")
         e = by_name.setdefault("gemm_tf32x3_kernel" if name in family else name,
                                {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
         e["time"] += tot / reps
@@ -225,6 +226,14 @@ def measure(model, runner, dev_pool, device, world, ms_per_step=None, batches_in
             ho, wo = (h_ - 1) // st_ + 1, (w_ - 1) // st_ + 1
             e["flops"] += 2.0 * b_ * ho * wo * 9 * ci_ * co_ * (cnt // reps)
             e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 2 * 9 * ci_ * co_ + b_ * ho * wo * co_) * (cnt // reps)
+        if name == "conv3x3_planes_tma":  # (b, h, w, cin, cout, stride, ldx, BN, relu, ldy, ldh): FP16 planes in (2 x 2 bytes per element)
+            b_, h_, w_, ci_, co_, st_ = ints[:6]
+            ho, wo = (h_ - 1) // st_ + 1, (w_ - 1) // st_ + 1
+            e["flops"] += 2.0 * b_ * ho * wo * 9 * ci_ * co_ * (cnt // reps)
+            e["bytes"] += 4.0 * (b_ * h_ * w_ * ci_ + 9 * ci_ * co_ + b_ * ho * wo * co_) * (cnt // reps)
+        if name == "gemm_planes_tma":  # (L, K, N, ldx, BN, relu, pool, ldy, ldh)
+            e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
+            e["bytes"] += 4.0 * (ints[0] * ints[1] + ints[1] * ints[2] + ints[0] // max(ints[6], 1) * ints[2]) * (cnt // reps)
         if name == "gemm_tf32x3_cm":  # (L, K, N, pts, ldx, BN, relu)
             e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
             e["bytes"] += 4.0 * (ints[0] * ints[1] + 2 * ints[1] * ints[2] + ints[0] * ints[2]) * (cnt // reps)
@@ -241,7 +250,7 @@ def measure(model, runner, dev_pool, device, world, ms_per_step=None, batches_in
         bn_at = {"gemm_tf32x3": 4, "conv3x3_nhwc_tf32x3": 6, "deconv_nhwc_tf32x3": 7}.get(name)
         if e["flops"] > before:
             from epnet_b200 import gemm as _g
-            f16 = bn_at is not None and _g.F16_WIDE and ints[bn_at] > 64
+            f16 = (bn_at is not None and _g.F16_WIDE and ints[bn_at] > 64) or name.endswith("_planes_tma")
             e["ideal_tf32_flops"] = e.get("ideal_tf32_flops", 0.0) + 3.0 * (e["flops"] - before) * (0.5 if f16 else 1.0)
     bf16_peak = 1383.2
     try:

@@ -245,8 +245,23 @@ class BackboneRunner:
                     return buf
 
                 img_channels = []
-                for conv1, conv2 in self.img_blocks_pm:
-                    x = run_conv(conv2, run_conv(conv1, x, True), False)
+                # Planes chain: every convolution after the first reads its input as the two FP16 planes the previous one's epilogue
+                # wrote, through TMA tensor loads (gemm.Planes, csrc gemm_f16x3_tma_kernel): each activation is split once, by its
+                # producer, instead of once per tap and column tile by the consumers' SIMT producer warps.  Needs the FP16 split
+                # to be on (range guard: overflowed()) and channel counts that are multiples of 64 (a k-block = one tap x 64 channels).
+                chain = self.f16 and all(c1.cout % 64 == 0 and c2.planes_capable() for c1, c2 in self.img_blocks_pm) and \
+                    all(c1.planes_capable() for c1, _ in self.img_blocks_pm[1:])
+                planes = None
+                for bi, (conv1, conv2) in enumerate(self.img_blocks_pm):
+                    if chain:
+                        _, mid = conv1(x if bi == 0 else planes, relu=True, planes_out=True, f32_out=False)
+                        last = bi + 1 == len(self.img_blocks_pm)
+                        if last:
+                            x = conv2(mid, relu=False)
+                        else:
+                            x, planes = conv2(mid, relu=False, planes_out=True)
+                    else:
+                        x = run_conv(conv2, run_conv(conv1, x, True), False)
                     ev = torch.cuda.Event()
                     ev.record(self.s_img)
                     imgs.append(x)

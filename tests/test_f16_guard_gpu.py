@@ -78,14 +78,22 @@ def test_backbone_falls_back_to_tf32_when_activations_leave_fp16_range():
         xyz_2, f_2 = model(data["points"], data["image"], data["xy"].clone())     # stays on the TF32 runner
     torch.cuda.synchronize()
     assert bool(torch.isfinite(f_f).all()) and torch.equal(xyz_f, xyz_m)
-    scale = f_m.abs().max().item()
-    assert (f_f - f_m).abs().max().item() <= 2e-5 * scale
     assert torch.equal(f_2, f_f)
+    # the fallback IS the TF32-split runner: bit-identical to a runner built with f16=False from the start
+    tf32 = model.make_runner(2, 16384, torch.device("cuda"), f16=False)
+    _, f_t = tf32(data["points"], data["image"], data["xy"])
+    torch.cuda.synchronize()
+    assert torch.equal(f_t, f_f)
+    # against the module path (cuDNN fp32).  This synthetic network is ill-conditioned by construction: activations of ~1e6 feed
+    # sums that cancel down to the output scale (~1e3), so fp32 rounding (1e-7 * 1e6) shows up as ~1e-3 of the output scale in
+    # EITHER implementation; the bound below is that conditioning, not the kernels' accuracy (tests/test_reference_python_gpu.py).
+    scale = f_m.abs().max().item()
+    assert (f_f - f_m).abs().max().item() <= 1e-2 * scale
     # the unguarded FP16 runner really does break on this model: its output is not finite or far off
     gemm.OverflowFlag(torch.device("cuda")).reset()
     raw = model.make_runner(2, 16384, torch.device("cuda"), f16=True)
     _, f_raw = raw(data["points"], data["image"], data["xy"])
     assert raw.overflowed()
-    bad = (~torch.isfinite(f_raw)).any().item() or (f_raw - f_m).abs().max().item() > 1e-3 * scale
+    bad = (~torch.isfinite(f_raw)).any().item() or (f_raw - f_m).abs().max().item() > 0.1 * scale
     assert bad, "expected the FP16 split to fail on activations beyond 65504"
     raw.overflow.reset()
