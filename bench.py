@@ -117,31 +117,38 @@ def timed_region(fn, steps, rank_sync, drain=None):
 
 
 def cpu_baseline_leg(sample_scenes=1, budget_s=15.0):
-    """Pure-PyTorch CPU implementation of the same backbone (oracle/torch_cpu.py ops + torch CPU convs) on
-    `sample_scenes` scene(s) of the workload, all host cores."""
-    from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
-    from epnet_b200.pointnet2_utils import make_ops
+    """BASELINE.json's first baseline: a pure-PyTorch CPU implementation of the same ops, on the box's host cores -- the reference's own,
+    unmodified Python (baseline/_ref: lib/net/pointnet2_msg.py::Pointnet2MSG over its pointnet2_modules / pointnet2_utils) with
+    `pointnet2_cuda` served by oracle/torch_cpu.py (vectorised torch CPU ops) and torch's CPU grid_sample / convolutions, on
+    `sample_scenes` scene(s) of the workload."""
+    import contextlib
+    from baseline import ref_env
+    from epnet_b200 import scenes
     from oracle import torch_cpu
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-
-    def cpu_gather(fm, xy):
-        return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
-
-    model = Pointnet2MSG(config=BackboneConfig(), ops=make_ops(torch_cpu), feature_gather=cpu_gather,
-                         reference_composition=True).eval()
-    data = scenes.batch(1000, sample_scenes, NPOINTS)
-    with torch.no_grad():
-        model(data["points"], data["image"], data["xy"].clone())  # warm-up: thread pool, oneDNN primitive caches, allocator
-        runs, t0 = 0, time.perf_counter()
-        while runs < 12 and (runs < 3 or time.perf_counter() - t0 < budget_s):
-            model(data["points"], data["image"], data["xy"].clone())
-            runs += 1
-        dt = (time.perf_counter() - t0) / runs
+    with contextlib.redirect_stdout(sys.stderr):
+        ref = ref_env.import_reference("reference")
+        torch.manual_seed(0)
+        model = ref.pointnet2_msg.Pointnet2MSG(input_channels=0, use_xyz=True).eval()
+    saved = (ref.pointnet2_utils.pointnet2, torch.cuda.FloatTensor, torch.cuda.IntTensor)
+    ref.pointnet2_utils.pointnet2 = torch_cpu  # pointnet2_utils.py:7; the op wrappers allocate with the legacy torch.cuda.* constructors
+    torch.cuda.FloatTensor = lambda *s: torch.empty(*s, dtype=torch.float32)
+    torch.cuda.IntTensor = lambda *s: torch.empty(*s, dtype=torch.int32)
+    try:
+        data = scenes.batch(1000, sample_scenes, NPOINTS)
+        with torch.no_grad():
+            model(data["points"], data["image"], data["xy"].clone())  # warm-up: thread pool, oneDNN primitive caches, allocator
+            runs, t0 = 0, time.perf_counter()
+            while runs < 12 and (runs < 3 or time.perf_counter() - t0 < budget_s):
+                model(data["points"], data["image"], data["xy"].clone())
+                runs += 1
+            dt = (time.perf_counter() - t0) / runs
+    finally:
+        ref.pointnet2_utils.pointnet2, torch.cuda.FloatTensor, torch.cuda.IntTensor = saved
     return {"value": round(sample_scenes / dt, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
-            "sample": "%d scene(s) of the batch: 1 warm-up + %d timed full backbone forwards (mean), pure-PyTorch CPU ops "
-                      "(oracle/torch_cpu.py) + torch CPU convolutions, all host cores" % (sample_scenes, runs),
+            "sample": "%d scene(s) of the batch: 1 warm-up + %d timed full backbone forwards (mean); the reference's own Python modules with "
+                      "pure-PyTorch CPU ops (oracle/torch_cpu.py) + torch CPU convolutions / grid_sample, all host cores" % (sample_scenes, runs),
             "seconds_per_forward": round(dt, 3)}
 
 
@@ -156,7 +163,6 @@ def main():
     ap.add_argument("--no-latency-leg", action="store_true", help="skip the one-batch-at-a-time measurement")
     ap.add_argument("--no-graph", action="store_true", help="ours: run eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--pipeline", type=int, default=8, help="ours: batches kept in flight (PipelinedRunner depth; 1 = one at a time)")
-    ap.add_argument("--layout", choices=["pm", "cm"], default="pm")
     ap.add_argument("--mode", choices=["infer", "train"], default="infer",
                     help="train = BASELINE.json configs[2]: forward+backward+Adam through the module path, train-mode BN, DDP gradient "
                          "all-reduce over NCCL when launched under torchrun (batch 2 per GPU)")
@@ -201,7 +207,7 @@ def main():
     image_key = ["image"]  # which host image step_e2e uploads: the reference's fp32 tensor, or the decoded uint8 frame
 
     use_graph = not args.no_graph and args.mode == "infer"
-    runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device, layout=args.layout, pipeline=args.pipeline) if use_graph else None
+    runner = model.make_runner(BATCH_PER_GPU, NPOINTS, device, pipeline=args.pipeline) if use_graph else None
     depth = args.pipeline if runner is not None else 1
 
     train_model = opt = None
@@ -324,7 +330,7 @@ def main():
                    "batch_per_gpu": BATCH_PER_GPU, "npoints": NPOINTS, "tf32": bool(args.tf32),
                    "l2": "inputs rotate over a %d-batch resident pool (%.0f MB > 126 MB L2)" % (POOL, POOL * h2d_bytes / 1e6),
                    "parallelism": "dp%d (independent scenes per GPU, no collective in the forward)" % world,
-                   "cuda_graph": bool(runner is not None), "layout": args.layout if runner is not None else "module path",
+                   "cuda_graph": bool(runner is not None), "layout": "pm" if runner is not None else "module path",
                    "batches_in_flight": depth,
                    "note": "ms_per_step = timed region / steps (throughput); with batches_in_flight > 1 successive steps overlap on the GPU"},
         "e2e": {"value": round(scenes_total / (ms_e2e / 1e3), 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,

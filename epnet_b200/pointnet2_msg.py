@@ -1,7 +1,8 @@
 """EPNet's two-stream RPN backbone (PointNet++ MSG point stream + image stream + LI-Fusion), mirroring
 /root/reference/lib/net/pointnet2_msg.py: same class and attribute names (so state dicts interchange),
 same forward signature and return values.  The point ops and the LI-Fusion gather run on the B200
-kernels; the dense image convolutions stay with cuDNN, as SURVEY.md section 8 scopes them.
+kernels.  In this op-by-op module path (training, drop-in use) the dense layers are torch modules, as in the reference; the
+inference runner (runner.py) runs them on the tcgen05 GEMM kernels too.
 
 Instead of the reference's process-global `cfg` (lib/config.py) the network is described by a
 BackboneConfig whose defaults are the published LI_Fusion_with_attention_use_ce_loss.yaml values;
@@ -15,7 +16,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import image_prep, li_fusion
-from . import pointnet2_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 
 
@@ -124,8 +124,7 @@ class Atten_Fusion_Conv(nn.Module):
 class Pointnet2MSG(nn.Module):
     """RPN backbone (pointnet2_msg.py:127-248)."""
 
-    def __init__(self, input_channels=None, use_xyz=None, config: BackboneConfig = None, ops=None, feature_gather=None,
-                 reference_composition=False):
+    def __init__(self, input_channels=None, use_xyz=None, config: BackboneConfig = None):
         super().__init__()
         c = config or BackboneConfig()
         if input_channels is not None:
@@ -133,16 +132,11 @@ class Pointnet2MSG(nn.Module):
         if use_xyz is not None:
             c.use_xyz = use_xyz
         self.config = c
-        # True: always run the reference's op-by-op composition (no fused kernels, no CUDA graph)
-        self.reference_composition = reference_composition
         # eval mode + torch.no_grad() + CUDA inputs: forward() transparently replays the captured inference runner, so
         # reference-style calling code gets the fast path without knowing about it (set False to force the module path)
         self.auto_fast_inference = True
         self._runner_cache = {}
         self._f16_ok = True
-        self._ops = ops or pointnet2_utils.OPS
-        # (feature_map (B,C,H,W), xy (B,N,2)) -> (B,C,N); the LI-Fusion boundary
-        self._feature_gather = feature_gather or (lambda fm, xy: li_fusion.feature_gather(fm, xy, c.align_corners))
 
         self.SA_modules = nn.ModuleList()
         channel_in = c.input_channels
@@ -152,7 +146,7 @@ class Pointnet2MSG(nn.Module):
             mlps = [[channel_in] + list(spec) for spec in c.mlps[k]]
             channel_out = sum(spec[-1] for spec in mlps)
             self.SA_modules.append(PointnetSAModuleMSG(npoint=c.npoints[k], radii=c.radius[k], nsamples=c.nsample[k],
-                                                       mlps=mlps, use_xyz=c.use_xyz, bn=c.use_bn, ops=self._ops))
+                                                       mlps=mlps, use_xyz=c.use_xyz, bn=c.use_bn))
             skip_channel_list.append(channel_out)
             channel_in = channel_out
 
@@ -179,20 +173,16 @@ class Pointnet2MSG(nn.Module):
         self.FP_modules = nn.ModuleList()
         for k in range(len(c.fp_mlps)):
             pre_channel = c.fp_mlps[k + 1][-1] if k + 1 < len(c.fp_mlps) else channel_out
-            self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k]),
-                                                    ops=self._ops))
+            self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k])))
 
-    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", pipeline=1, f16=True):
+    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, pipeline=1, f16=True):
         """Inference fast path (eval mode): one CUDA graph with the FPS chain, the image stream and the point
         stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py.
         f16=False keeps every GEMM on the TF32 operand split (fp32 range; see BackboneRunner)."""
-        if self.reference_composition:
-            raise RuntimeError("reference_composition=True pins the op-by-op path")
         from .runner import BackboneRunner, PipelinedRunner
         if pipeline > 1:
-            return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, layout=layout,
-                                   f16=f16)
-        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, layout=layout, f16=f16)
+            return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, f16=f16)
+        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, f16=f16)
 
     @staticmethod
     def _break_up_pc(pc):
@@ -241,9 +231,9 @@ class Pointnet2MSG(nn.Module):
         normalised and zero-padded to the 384x1280 canvas on the device (image_prep.py) instead of on the host in float64
         (lib/datasets/kitti_dataset.py:37-57)."""
         c = self.config
-        if (self.auto_fast_inference and not self.training and not torch.is_grad_enabled() and not self.reference_composition
+        if (self.auto_fast_inference and not self.training and not torch.is_grad_enabled()
                 and c.li_fusion and c.input_channels == 0 and image is not None and xy is not None and pointcloud.is_cuda
-                and pointcloud.shape[-1] == 3 and self._ops is pointnet2_utils.OPS):
+                and pointcloud.shape[-1] == 3):
             return self._fast_forward(pointcloud, image, xy, sizes)
         if image is not None and image.dtype == torch.uint8:
             image = image_prep.normalise_pad(image if image.is_cuda else image.to(pointcloud.device), sizes)
@@ -262,7 +252,7 @@ class Pointnet2MSG(nn.Module):
                 gather_index = li_index.long().unsqueeze(-1).repeat(1, 1, 2)
                 li_xy_cor = torch.gather(l_xy_cor[i], 1, gather_index)
                 image = self.Img_Block[i](img[i])
-                img_gather_feature = self._feature_gather(image, li_xy_cor)
+                img_gather_feature = li_fusion.feature_gather(image, li_xy_cor, c.align_corners)  # the LI-Fusion boundary (pointnet2_msg.py:107-120)
                 li_features = self.Fusion_Conv[i](li_features, img_gather_feature)
                 l_xy_cor.append(li_xy_cor)
                 img.append(image)
@@ -275,7 +265,7 @@ class Pointnet2MSG(nn.Module):
         if c.li_fusion:
             de_concat = torch.cat([self.DeConv[i](img[i + 1]) for i in range(len(c.img_channels) - 1)], dim=1)
             img_fusion = F.relu(self.image_fusion_bn(self.image_fusion_conv(de_concat)))
-            img_fusion_gather_feature = self._feature_gather(img_fusion, xy)
+            img_fusion_gather_feature = li_fusion.feature_gather(img_fusion, xy, c.align_corners)
             l_features[0] = self.final_fusion_img_point(l_features[0], img_fusion_gather_feature)
 
         return l_xyz[0], l_features[0]

@@ -2,20 +2,17 @@
 (FurthestPointSampling, GatherOperation, ThreeNN, ThreeInterpolate, GroupingOperation, BallQuery and their lower-case
 `.apply` aliases) plus the QueryAndGroup / GroupAll modules -- same names, argument order and return values.
 
-Design: every op is described once by a pair of plain functions (launch, optional gradient launch) that receive a backend
-module exposing the nine `*_wrapper` entry points of the reference's pybind table; `make_ops(backend)` turns the table into
-`torch.autograd.Function` classes.  The module-level names are bound to epnet_b200.pointnet2_cuda (libepnet_b200.so);
-tests/ and bench.py's reference arm build a second set on the reference's own kernels through the same table -- the product
-never does.  Buffers the reference expects pre-filled (FPS scratch 1e10, zeroed ball-query indices, zeroed gradients) are
+Design: every op is described once by a pair of plain functions (launch, optional gradient launch) over the nine `*_wrapper`
+entry points of the reference's pybind table, served by epnet_b200.pointnet2_cuda (libepnet_b200.so) -- the only backend; a table
+turns them into `torch.autograd.Function` classes.  There is no backend parameter anywhere in the product: the CPU tests swap the
+module-level `_BACKEND` for the C oracle from tests/backend_swap.py.  Buffers the reference expects pre-filled (FPS scratch 1e10, zeroed ball-query indices, zeroed gradients) are
 prepared here, exactly where the reference's Python layer prepares them (pointnet2_utils.py:26, :218, :67/:146/:190).
 """
-from types import SimpleNamespace
-
 import torch
 import torch.nn as nn
 from torch.autograd import Function
 
-from . import pointnet2_cuda as _default_backend
+from . import pointnet2_cuda as _BACKEND  # the one backend; looked up at call time (tests/backend_swap.py replaces it on CPU)
 
 
 def _buf(like, *shape, dtype=torch.float32, fill=None):
@@ -128,59 +125,46 @@ _ALIASES = {"FurthestPointSampling": "furthest_point_sample", "GatherOperation":
             "ThreeInterpolate": "three_interpolate", "GroupingOperation": "grouping_operation", "BallQuery": "ball_query"}
 
 
-def _function_class(name, backend, launch, grad, arity):
+def _function_class(name, launch, grad, arity):
     def forward(ctx, *args):
-        return launch(backend, ctx, *args)
+        return launch(_BACKEND, ctx, *args)
 
     def backward(ctx, *grads):
-        first = grad(backend, ctx, grads[0]) if grad is not None else None
+        first = grad(_BACKEND, ctx, grads[0]) if grad is not None else None
         return (first,) + (None,) * (arity - 1)
 
     return type(name, (Function,), {"forward": staticmethod(forward), "backward": staticmethod(backward),
-                                    "__doc__": "%s of pointnet2_utils.py on backend %s" % (name, getattr(backend, "__name__", backend))})
+                                    "__doc__": "%s of pointnet2_utils.py on libepnet_b200.so" % name})
 
 
-def make_ops(backend):
-    """The op set on `backend`: namespace with the six Function classes, their `.apply` aliases and `.backend`."""
-    ops = SimpleNamespace(backend=backend)
-    for name, (launch, grad, arity) in _TABLE.items():
-        cls = _function_class(name, backend, launch, grad, arity)
-        setattr(ops, name, cls)
-        setattr(ops, _ALIASES[name], cls.apply)
-    return ops
-
-
-OPS = make_ops(_default_backend)
-for _name in _TABLE:  # module-level names, as the reference exposes them
-    globals()[_name] = getattr(OPS, _name)
-    globals()[_ALIASES[_name]] = getattr(OPS, _ALIASES[_name])
-del _name
+for _name, (_launch, _grad, _arity) in _TABLE.items():  # module-level names, as the reference exposes them
+    globals()[_name] = _function_class(_name, _launch, _grad, _arity)
+    globals()[_ALIASES[_name]] = globals()[_name].apply
+del _name, _launch, _grad, _arity
 
 
 class QueryAndGroup(nn.Module):
     """Ball query around every centre, then the members' coordinates (relative to the centre) and features, stacked on the
     channel axis (pointnet2_utils.py:231-264).  cloud (B,N,3), centres (B,M,3), feats (B,C,N) -> (B, 3+C, M, nsample)."""
 
-    def __init__(self, radius, nsample, use_xyz=True, ops=None):
+    def __init__(self, radius, nsample, use_xyz=True):
         super().__init__()
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
-        self._ops = ops or OPS
 
     def forward(self, xyz, new_xyz, features=None):
-        ops = self._ops
-        members = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
-        offsets = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), members) - new_xyz.transpose(1, 2).unsqueeze(-1)
+        members = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        offsets = grouping_operation(xyz.transpose(1, 2).contiguous(), members) - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
             return offsets
-        picked = ops.grouping_operation(features, members)
+        picked = grouping_operation(features, members)
         return torch.cat([offsets, picked], dim=1) if self.use_xyz else picked
 
 
 class GroupAll(nn.Module):
     """One group holding the whole cloud (pointnet2_utils.py:267-290): (B,N,3), _, (B,C,N) -> (B, 3+C, 1, N)."""
 
-    def __init__(self, use_xyz=True, ops=None):
+    def __init__(self, use_xyz=True):
         super().__init__()
         self.use_xyz = use_xyz
 

@@ -41,17 +41,16 @@ def _select_band(in_band, quota, skip):
     return src[:, :quota], count
 
 
-def select_proposals(scores, proposals, pre_nms_top_n, post_nms_top_n, nms_thresh, distance_based=True, nms_type="rotate",
-                     nms=None):
+def select_proposals(scores, proposals, pre_nms_top_n, post_nms_top_n, nms_thresh, distance_based=True, nms_type="rotate"):
     """scores (B,N), proposals (B,N,7) [x, y, z, h, w, l, ry] -> ret_bbox3d (B, post_nms_top_n, 7), ret_scores (B, post_nms_top_n),
     zero-padded, as `ProposalLayer.forward` returns them (proposal_layer.py:39-56).  nms_type: 'rotate' | 'normal'
-    (cfg.RPN.NMS_TYPE, lib/config.py:90).  `nms` defaults to iou3d_utils.nms_batched (tests inject a checker with the same
-    interface)."""
+    (cfg.RPN.NMS_TYPE, lib/config.py:90).  The NMS is iou3d_utils.nms_batched (libepnet_b200.so); the CPU tests replace that
+    module attribute with the oracle (tests/backend_swap.py)."""
     if nms_type not in ("rotate", "normal"):
         raise NotImplementedError(nms_type)           # proposal_layer.py:108-109
     if scores.dim() != 2 or proposals.shape != scores.shape + (7,):
         raise ValueError("scores must be (B,N) and proposals (B,N,7)")
-    nms = nms or iou3d_utils.nms_batched
+    nms = iou3d_utils.nms_batched  # looked up at call time
     B, N = scores.shape
     dev = scores.device
     order = torch.sort(scores, dim=1, descending=True)[1]

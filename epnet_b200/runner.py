@@ -3,7 +3,7 @@
 
 What changes relative to the op-by-op module path (nothing changes in WHAT is computed):
   * three streams inside ONE captured CUDA graph: the furthest-point-sampling chain of all four levels (it
-    depends on coordinates only), the image stream (cuDNN convolutions), and the point stream; the ~300 tiny
+    depends on coordinates only), the image stream, and the point stream; the ~300 tiny
     launches of a forward become one graph replay with parallel branches;
   * eval-mode BatchNorm is folded into the preceding convolution / 1x1 conv (w' = w*g/sqrt(v+eps),
     b' = beta - mean*g/sqrt(v+eps));
@@ -11,15 +11,30 @@ What changes relative to the op-by-op module path (nothing changes in WHAT is co
     ball-query indices feed one group+recentre+concat launch that writes the GEMM operand; the last MLP
     layer's bias+ReLU is fused with the max-pool and writes into the multi-scale concat; three_nn distances
     feed one weights+interpolate+concat launch;
-  * shared 1x1 convolutions run as batched GEMMs (cuBLAS, strict fp32) on (B, C, L) operands.
+  * every shared-MLP layer, 3x3 convolution, transposed convolution and fusion layer runs on the hand-written tcgen05 GEMM
+    kernels (csrc/gemm_tf32x3.cu) over point-major / NHWC activations -- no cuBLAS or cuDNN call anywhere in the runner.
 Only eval mode is supported here (train mode needs batch statistics: use the module path).
 """
 import torch
-import torch.nn.functional as F
 
 from . import image_prep
 from . import pointnet2_cuda as pc
 from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
+
+
+class _nvtx:
+    """NVTX range around a level of the schedule (the reference has no profiler hooks).  Host-side markers:
+    they label the eager pass and the capture under Nsight Systems / Compute (`--nvtx --nvtx-include "SA1/"`), cost nothing in a replay."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _fold_bn(weight2d, conv_bias, bn):
@@ -43,36 +58,6 @@ def _fold_shared_mlp(mlp):
             bias = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=w2d.device)
             layers.append((w2d.contiguous(), bias.contiguous()))
     return layers
-
-
-class _Fusion:
-    """Folded parameters of Atten_Fusion_Conv / Fusion_Conv (lib/net/pointnet2_msg.py:35-104)."""
-
-    def __init__(self, mod):
-        self.attention = hasattr(mod, "IA_Layer")
-        if self.attention:
-            ia = mod.IA_Layer
-            self.w1, self.b1 = ia.fc1.weight.contiguous(), ia.fc1.bias
-            self.w2, self.b2 = ia.fc2.weight.contiguous(), ia.fc2.bias
-            self.w3, self.b3 = ia.fc3.weight.contiguous(), ia.fc3.bias
-            conv, bn = ia.conv1[0], ia.conv1[1]
-            self.wc, self.bc = _fold_bn(conv.weight.squeeze(-1), conv.bias, bn)
-        w, b = _fold_bn(mod.conv1.weight.squeeze(-1), mod.conv1.bias, mod.bn1)
-        self.wf, self.bf = w, b
-
-    def __call__(self, point, img):
-        """point (B,Cp,M), img (B,Ci,M) -> (B,Cp,M)"""
-        B, _, M = point.shape
-        if self.attention:
-            r = torch.matmul(self.w1, img) + torch.matmul(self.w2, point) + (self.b1 + self.b2)[:, None]
-            att = torch.sigmoid(torch.matmul(self.w3, torch.tanh(r)) + self.b3[:, None])  # (B,1,M)
-            img_new = torch.matmul(self.wc, img)
-            pc.bias_relu_wrapper(B, img_new.shape[1], M, img_new, self.bc)
-            img = img_new * att
-        out = torch.matmul(self.wf, torch.cat([point, img], dim=1))
-        pc.bias_relu_wrapper(B, out.shape[1], M, out, self.bf)
-        return out
-
 
 
 class _FusionPM:
@@ -106,16 +91,14 @@ class _FusionPM:
         return self.fuse(cat, relu=True, out=out, out_cm=out_cm)
 
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, layout="pm", tiles="latency", f16=True):
-        """layout "pm": point-major activations + tcgen05 fp32-grade GEMMs (default); "cm": channel-major + cuBLAS.
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True):
+        """Point-major activations + tcgen05 fp32-grade GEMMs.
         f16: the wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE), which needs activations and folded weights
         below 65504 in magnitude (they are below 10 for the published configuration).  Guarded twice: a layer whose folded
         weights leave the range is packed for the TF32 split (PackedLinear.f16_ok), and every GEMM epilogue raises a device flag
         on |y| > 6e4 / non-finite values, read back with every call (`overflowed()`); Pointnet2MSG.forward and PipelinedRunner
         callers then switch to f16=False (TF32 split everywhere: fp32's range).  EPNET_F16_WIDE=0 forces that from the start.
         tiles: gemm.tile_policy for every GEMM launch of this runner ("latency" for one batch at a time)."""
-        assert layout in ("pm", "cm")
-        self.layout = layout
         self.tiles = tiles
         self.f16 = bool(f16)
         self.overflow = OverflowFlag(device)
@@ -134,7 +117,6 @@ class BackboneRunner:
         # front of the replay by one kernel from whatever the caller holds (image_prep.py): the decoded uint8 image, or the
         # reference's fp32 (B,3,H,W) tensor.  Staging buffers for host inputs are allocated on first use.
         self.image4 = torch.zeros(batch, H, W, 4, **f32)
-        self.image = torch.zeros(batch, 3, H, W, **f32) if layout == "cm" else None
         self._stage_f32 = None
         self._stage_u8 = None
         self.xy = torch.zeros(batch, npoints, 2, **f32)
@@ -153,13 +135,8 @@ class BackboneRunner:
                 for blk in model.Img_Block:
                     w1, b1 = _fold_bn(blk.conv1.weight.flatten(1), None, blk.bn1)
                     self.img_blocks.append((w1.view_as(blk.conv1.weight).contiguous(), b1, blk.conv1.stride, blk.conv2))
-                self.fusion = [_Fusion(m) for m in model.Fusion_Conv]
-                self.final_fusion = _Fusion(model.final_fusion_img_point)
-                wq, bq = _fold_bn(model.image_fusion_conv.weight.flatten(1), model.image_fusion_conv.bias, model.image_fusion_bn)
-                self.img_fuse_w, self.img_fuse_b = wq.view_as(model.image_fusion_conv.weight).contiguous(), bq
 
-            if layout == "pm":
-                self._build_pm()
+            self._build_pm()
 
         self.s_fps = torch.cuda.Stream(device=device)
         self.s_img = torch.cuda.Stream(device=device)
@@ -172,24 +149,6 @@ class BackboneRunner:
             self._capture()
 
     # ------------------------------------------------------------------------------------ pieces
-    def _mlp_pool(self, x, layers, B, M, ns, out_buf, c_off):
-        """x (B,Cin,M*ns) -> max over ns of the shared MLP, written into out_buf[:, c_off:c_off+Cout, :]."""
-        L = M * ns
-        for li, (w, b) in enumerate(layers):
-            x = torch.matmul(w, x)  # (B,Cout,L) batched GEMM, strict fp32
-            if li + 1 < len(layers):
-                pc.bias_relu_wrapper(B, w.shape[0], L, x, b)
-        cout = layers[-1][0].shape[0]
-        pc.bias_relu_maxpool_wrapper(B, cout, M, ns, x, layers[-1][1], out_buf.data_ptr() + 4 * c_off * M,
-                                     out_buf.shape[1] * M)
-        return cout
-
-    def _mlp(self, x, layers, B, L):
-        for w, b in layers:
-            x = torch.matmul(w, x)
-            pc.bias_relu_wrapper(B, w.shape[0], L, x, b)
-        return x
-
     def _forward(self):
         with tile_policy(self.tiles), f16_split(self.f16):
             return self._forward_impl()
@@ -200,14 +159,13 @@ class BackboneRunner:
         f32 = dict(dtype=torch.float32, device=dev)
         xyz0 = self.points
         xyn = self.xy / self._xy_scale * 2.0 - 1.0 if c.li_fusion else None  # pointnet2_msg.py:208-210
-        pm = self.layout == "pm"
 
         # ---- FPS chain of all levels (coordinates only) on its own stream ----
         ready = torch.cuda.Event()
         ready.record(main)
         self._ready = ready
         l_xyz, l_xy, fps_done = [xyz0], [xyn], []
-        with torch.cuda.stream(self.s_fps):
+        with torch.cuda.stream(self.s_fps), _nvtx("fps_chain"):
             self.s_fps.wait_event(ready)
             cur_xyz, cur_xy = xyz0, xyn
             for npoint, _ in self.sa:
@@ -226,9 +184,9 @@ class BackboneRunner:
 
         # ---- image stream ----
         imgs, img_done, img_fusion, img_fusion_done = [], [], None, None
-        if c.li_fusion and pm:
+        if c.li_fusion:
             # NHWC activations; 3x3 convolutions, transposed convolutions and the 1x1 fusion conv on the tcgen05 3xTF32 GEMM
-            with torch.cuda.stream(self.s_img):
+            with torch.cuda.stream(self.s_img), _nvtx("image_stream"):
                 self.s_img.wait_event(ready)
                 H, W = self.image4.shape[1], self.image4.shape[2]
                 x = self.image4
@@ -276,80 +234,12 @@ class BackboneRunner:
                 img_fusion = self.img_fuse_pm(cat.view(-1, self.deconv_cat_width), relu=True).view(B, H, W, -1)
                 img_fusion_done = torch.cuda.Event()
                 img_fusion_done.record(self.s_img)
-        elif c.li_fusion:
-            with torch.cuda.stream(self.s_img):
-                self.s_img.wait_event(ready)
-                x = self.image
-                for (w1, b1, stride, conv2) in self.img_blocks:
-                    x = F.conv2d(x, w1, None, stride=stride, padding=1)
-                    pc.bias_relu_wrapper(B, x.shape[1], x.shape[2] * x.shape[3], x, b1)  # folded BN bias + ReLU, one pass
-                    x = conv2(x)
-                    ev = torch.cuda.Event()
-                    ev.record(self.s_img)
-                    imgs.append(x)
-                    img_done.append(ev)
-                de = torch.cat([self.model.DeConv[i](imgs[i]) for i in range(len(imgs))], dim=1)
-                img_fusion = F.conv2d(de, self.img_fuse_w, None)
-                pc.bias_relu_wrapper(B, img_fusion.shape[1], img_fusion.shape[2] * img_fusion.shape[3], img_fusion, self.img_fuse_b)
-                img_fusion_done = torch.cuda.Event()
-                img_fusion_done.record(self.s_img)
-
-        if pm:
-            feats = self._point_stream_pm(main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn)
-            main.wait_stream(self.s_fps)
-            main.wait_stream(self.s_img)
-            for st in self.s_geo + self.s_scale:
-                main.wait_stream(st)
-            return xyz0, feats
-
-        # ---- point stream (channel-major, cuBLAS) ----
-        l_feat = [None]
-        for k, (npoint, scales) in enumerate(self.sa):
-            main.wait_event(fps_done[k])
-            xyz, new_xyz, feats = l_xyz[k], l_xyz[k + 1], l_feat[k]
-            n = xyz.shape[1]
-            cin = 0 if feats is None else feats.shape[1]
-            ctot = sum(layers[-1][0].shape[0] for _, _, layers in scales)
-            out = torch.empty((B, ctot, npoint), **f32)
-            c_off = 0
-            for radius, ns, layers in scales:
-                bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
-                pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
-                grouped = torch.empty((B, 3 + cin, npoint * ns), **f32)
-                pc.group_concat_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, feats, bidx, grouped)
-                c_off += self._mlp_pool(grouped, layers, B, npoint, ns, out, c_off)
-            if c.li_fusion:
-                main.wait_event(img_done[k])
-                img = imgs[k]
-                gathered = torch.empty((B, img.shape[1], npoint), **f32)
-                pc.grid_gather_bilinear_wrapper(B, img.shape[1], img.shape[2], img.shape[3], npoint, img, l_xy[k + 1],
-                                                c.align_corners, gathered)
-                out = self.fusion[k](out, gathered)
-            l_feat.append(out)
-
-        for i in range(-1, -(len(self.fp) + 1), -1):
-            unknown, known = l_xyz[i - 1], l_xyz[i]
-            n, m = unknown.shape[1], known.shape[1]
-            skip, kf = l_feat[i - 1], l_feat[i]
-            c1 = 0 if skip is None else skip.shape[1]
-            dist2 = torch.empty((B, n, 3), **f32)
-            idx3 = torch.empty((B, n, 3), dtype=torch.int32, device=dev)
-            pc.three_nn_wrapper(B, n, m, unknown, known, dist2, idx3)
-            cat = torch.empty((B, kf.shape[1] + c1, n), **f32)
-            pc.three_interpolate_concat_wrapper(B, kf.shape[1], m, n, c1, kf, idx3, dist2, skip, cat)
-            l_feat[i - 1] = self._mlp(cat, self.fp[i], B, n)
-
-        feats = l_feat[0]
-        if c.li_fusion:
-            main.wait_event(img_fusion_done)
-            g = torch.empty((B, img_fusion.shape[1], N), **f32)
-            pc.grid_gather_bilinear_wrapper(B, img_fusion.shape[1], img_fusion.shape[2], img_fusion.shape[3], N, img_fusion, xyn,
-                                            c.align_corners, g)
-            feats = self.final_fusion(feats, g)
+        feats = self._point_stream_pm(main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn)
         main.wait_stream(self.s_fps)
         main.wait_stream(self.s_img)
+        for st in self.s_geo + self.s_scale:
+            main.wait_stream(st)
         return xyz0, feats
-
 
     # ------------------------------------------------------------------------------------ point-major path
     def _build_pm(self):
@@ -429,6 +319,7 @@ class BackboneRunner:
 
         l_feat = [None]  # (B*n_k, C_k) point-major
         for k, (npoint, scales) in enumerate(self.sa_pm):
+            torch.cuda.nvtx.range_push("SA%d" % (k + 1))
             main.wait_event(fps_done[k])
             xyz, new_xyz, feats = l_xyz[k], l_xyz[k + 1], l_feat[k]
             n = xyz.shape[1]
@@ -480,6 +371,7 @@ class BackboneRunner:
                 l_feat.append(self.fusion_pm[k](cat, g))
             else:
                 l_feat.append(cat)
+            torch.cuda.nvtx.range_pop()
 
         for i in range(-1, -(len(self.fp_pm) + 1), -1):
             unknown, known = l_xyz[i - 1], l_xyz[i]
@@ -488,6 +380,7 @@ class BackboneRunner:
             c1 = 0 if skip is None else skip.shape[1]
             c2 = kf.shape[1]
             wts, idx3, nn_ev = nn[len(self.fp_pm) + i]  # searched on the geometry stream right after the FPS level
+            torch.cuda.nvtx.range_push("FP%d" % (len(self.fp_pm) + i))
             main.wait_event(nn_ev)
             x = torch.empty((B * n, c2 + c1), **f32)
             pc.three_interpolate_concat_pm_wrapper(B, c2, m, n, c1, kf, idx3, wts, skip, x)
@@ -499,6 +392,7 @@ class BackboneRunner:
             for lin in lins[:-1]:
                 x = lin(x, relu=True)
             l_feat[i - 1] = lins[-1](x, relu=True, out=last_out)
+            torch.cuda.nvtx.range_pop()
 
         feats = l_feat[0]
         if c.li_fusion:
@@ -538,11 +432,7 @@ class BackboneRunner:
                 image = self._stage_u8
             if sizes is not None and not sizes.is_cuda:
                 sizes = sizes.to(self.device, non_blocking=True)
-            image_prep.normalise_pad(image, sizes, out_hw=tuple(self.image4.shape[1:3]), nhwc4=self.image4,
-                                     nchw=self.image if self.layout == "cm" else None)
-            return
-        if self.layout == "cm":
-            self.image.copy_(image, non_blocking=True)
+            image_prep.normalise_pad(image, sizes, out_hw=tuple(self.image4.shape[1:3]), nhwc4=self.image4)
             return
         if not image.is_cuda or not image.is_contiguous():
             if self._stage_f32 is None:

@@ -37,19 +37,16 @@ def _close(a, b, rel):
 
 
 def test_module_path_equals_reference_kernels():
-    from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
-    from epnet_b200.pointnet2_utils import make_ops
-    from oracle import ref_cuda
-    if not ref_cuda.available():
-        pytest.skip("oracle/_ref not built")
+    """our op-by-op module path == the reference's own, unmodified Python (baseline/_ref) on the reference's own kernels"""
+    from baseline import ref_env
+    from epnet_b200 import scenes
+    if not ref_env.staged():
+        pytest.skip("baseline/_ref not staged")
     _strict_fp32()
     ours = _models()
-
-    def aten_gather(fm, xy):
-        return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
-
-    ref = Pointnet2MSG(config=BackboneConfig(), ops=make_ops(ref_cuda), feature_gather=aten_gather, reference_composition=True).cuda().eval()
-    ref.load_state_dict(ours.state_dict())
+    ref_mods = ref_env.import_reference("reference")
+    ref = ref_mods.pointnet2_msg.Pointnet2MSG(input_channels=0, use_xyz=True).cuda().eval()
+    ref.load_state_dict(ours.state_dict(), strict=True)
     data = {k: v.cuda() for k, v in scenes.batch(1000, 2, 16384).items()}
     with torch.no_grad():
         xyz_o, f_o = ours(data["points"], data["image"], data["xy"].clone())
@@ -59,12 +56,12 @@ def test_module_path_equals_reference_kernels():
     _close(f_o, f_r, 1e-5)
 
 
-@pytest.mark.parametrize("layout,use_graph", [("pm", False), ("pm", True), ("cm", True)])
-def test_runner_equals_module_path(layout, use_graph):
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_runner_equals_module_path(use_graph):
     from epnet_b200 import scenes
     _strict_fp32()
     ours = _models()
-    runner = ours.make_runner(2, 16384, torch.device("cuda"), use_graph=use_graph, layout=layout)
+    runner = ours.make_runner(2, 16384, torch.device("cuda"), use_graph=use_graph)
     for seed in (1000, 1020):
         data = {k: v.cuda() for k, v in scenes.batch(seed, 2, 16384).items()}
         with torch.no_grad():
@@ -78,7 +75,7 @@ def test_runner_equals_module_path(layout, use_graph):
         # BN folding and GEMM re-association move results by a few fp32 ulps per layer; the tcgen05 3xTF32 GEMMs of the
         # point-major path stay below 3e-6 per layer even at K=1536 (tests/test_gemm_gpu.py)
         err = (f_r - f_m).abs().max().item() / f_m.abs().max().item()
-        print("runner[%s] vs module path: max abs err / output scale = %.2e" % (layout, err))
+        print("runner[graph=%s] vs module path: max abs err / output scale = %.2e" % (use_graph, err))
         _close(f_r, f_m, 2e-5)
 
 

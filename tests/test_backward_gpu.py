@@ -1,5 +1,5 @@
 """Training-mode parity (BASELINE.json configs[2] path on one GPU): forward + backward through the module path on the B200
-kernels vs the same modules on the reference's own kernels + ATen grid_sample.  Train-mode BatchNorm (batch statistics),
+kernels vs the reference's own unmodified Python modules (baseline/_ref) on the reference's own kernels + ATen grid_sample.  Train-mode BatchNorm (batch statistics),
 strict fp32.  The reference's backward kernels accumulate with unordered fp32 atomics (sampling_gpu.cu:62,
 group_points_gpu.cu:24, interpolate_gpu.cu:139-141) and so do ours: gradients agree to accumulation-order noise."""
 import pytest
@@ -9,22 +9,19 @@ pytestmark = pytest.mark.gpu
 
 
 def test_backbone_forward_backward_matches_reference_kernels():
+    from baseline import ref_env
     from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
-    from epnet_b200.pointnet2_utils import make_ops
-    from oracle import ref_cuda
-    if not ref_cuda.available():
-        pytest.skip("oracle/_ref not built")
+    if not ref_env.staged():
+        pytest.skip("baseline/_ref not staged")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.deterministic = True
 
-    def aten_gather(fm, xy):
-        return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
-
     torch.manual_seed(0)
     ours = Pointnet2MSG(config=BackboneConfig()).cuda().train()
-    ref = Pointnet2MSG(config=BackboneConfig(), ops=make_ops(ref_cuda), feature_gather=aten_gather, reference_composition=True).cuda().train()
-    ref.load_state_dict(ours.state_dict())
+    # the reference's own, unmodified Python (lib/net/pointnet2_msg.py) on the reference's own kernels + ATen grid_sample
+    ref = ref_env.import_reference("reference").pointnet2_msg.Pointnet2MSG(input_channels=0, use_xyz=True).cuda().train()
+    ref.load_state_dict(ours.state_dict(), strict=True)
     data = {k: v.cuda() for k, v in scenes.batch(3000, 2, 16384).items()}
     target = torch.randn(2, 128, 16384, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
 

@@ -7,17 +7,8 @@ import numpy as np
 import torch
 
 import oracle
+from backend_swap import cpu_oracle
 from golden_util import load, small_backbone_config, state_dict
-
-
-def _cpu_ops():
-    from epnet_b200.pointnet2_utils import make_ops
-    from oracle import cpu_backend
-    return make_ops(cpu_backend)
-
-
-def _cpu_gather(fm, xy):
-    return torch.nn.functional.grid_sample(fm, xy.unsqueeze(1), align_corners=False).squeeze(2)
 
 
 def test_oracle_reproduces_recorded_op_outputs():
@@ -35,14 +26,19 @@ def test_oracle_reproduces_recorded_op_outputs():
 
 def test_mirror_op_surface_matches_reference_python():
     g = load("ops_lidar2048.npz")
+    from epnet_b200 import pointnet2_utils as ops
     from epnet_b200.pointnet2_utils import QueryAndGroup
-    ops = _cpu_ops()
     pts, feats = torch.from_numpy(g["points"]), torch.from_numpy(g["feats"])
+    with cpu_oracle():
+        _op_surface_checks(g, ops, QueryAndGroup, pts, feats)
+
+
+def _op_surface_checks(g, ops, QueryAndGroup, pts, feats):
     idx = ops.furthest_point_sample(pts, 512)
     assert idx.dtype == torch.int32 and torch.equal(idx, torch.from_numpy(g["fps_idx"]))
     new_xyz = ops.gather_operation(pts.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
     assert torch.equal(new_xyz, torch.from_numpy(g["new_xyz"]))
-    qg = QueryAndGroup(0.8, 16, use_xyz=True, ops=ops)(pts, new_xyz, feats)
+    qg = QueryAndGroup(0.8, 16, use_xyz=True)(pts, new_xyz, feats)
     assert torch.equal(qg, torch.from_numpy(g["query_and_group"]))
     dist, nn_idx = ops.three_nn(pts, new_xyz)
     assert torch.equal(dist, torch.from_numpy(g["nn_dist"])) and torch.equal(nn_idx, torch.from_numpy(g["nn_idx"]))
@@ -51,14 +47,13 @@ def test_mirror_op_surface_matches_reference_python():
 def test_mirror_sa_and_fp_modules_match_reference_python():
     g = load("modules_sa_fp.npz")
     from epnet_b200.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
-    ops = _cpu_ops()
-    sa = PointnetSAModuleMSG(npoint=128, radii=[0.8, 1.6], nsamples=[16, 32], mlps=[[6, 8, 16], [6, 8, 24]], use_xyz=True, bn=True, ops=ops)
-    fp = PointnetFPModule(mlp=[40 + 6, 32, 16], ops=ops)
+    sa = PointnetSAModuleMSG(npoint=128, radii=[0.8, 1.6], nsamples=[16, 32], mlps=[[6, 8, 16], [6, 8, 24]], use_xyz=True, bn=True)
+    fp = PointnetFPModule(mlp=[40 + 6, 32, 16])
     sa.load_state_dict(state_dict(g, "sa."), strict=True)  # identical key names = checkpoint compatibility
     fp.load_state_dict(state_dict(g, "fp."), strict=True)
     sa.eval(); fp.eval()
     pts, feats = torch.from_numpy(g["points"]), torch.from_numpy(g["feats"])
-    with torch.no_grad():
+    with torch.no_grad(), cpu_oracle():
         new_xyz, new_feat, idx = sa(pts, feats)
         out = fp(pts, new_xyz, feats, new_feat)
     assert torch.equal(idx, torch.from_numpy(g["sa_idx"]))
@@ -70,11 +65,11 @@ def test_mirror_sa_and_fp_modules_match_reference_python():
 def test_mirror_backbone_matches_reference_python():
     g = load("backbone_small.npz")
     from epnet_b200 import Pointnet2MSG
-    net = Pointnet2MSG(config=small_backbone_config(), ops=_cpu_ops(), feature_gather=_cpu_gather, reference_composition=True)
+    net = Pointnet2MSG(config=small_backbone_config())
     net.load_state_dict(state_dict(g, "w."), strict=True)
     net.eval()
     xy = torch.from_numpy(g["xy"]).clone()
-    with torch.no_grad():
+    with torch.no_grad(), cpu_oracle():
         xyz, feat = net(torch.from_numpy(g["points"]), torch.from_numpy(g["image"]), xy)
     assert torch.equal(xy, torch.from_numpy(g["xy_after_call"]))  # the in-place normalisation of pointnet2_msg.py:209-210
     assert torch.equal(xyz, torch.from_numpy(g["out_xyz"]))

@@ -52,7 +52,7 @@ def test_sa_fp_modules_on_cuda():
     np.testing.assert_allclose(out.cpu().numpy(), g["fp_out"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("path", ["module", "runner_pm", "runner_cm"])
+@pytest.mark.parametrize("path", ["module", "runner"])
 def test_small_backbone_on_cuda(path):
     _strict()
     g = load("backbone_small.npz")
@@ -67,7 +67,7 @@ def test_small_backbone_on_cuda(path):
         if path == "module":
             xyz, feat = net(pts, img, xy.clone())
         else:
-            runner = net.make_runner(2, 1024, torch.device("cuda"), image_hw=(96, 320), layout=path[-2:])
+            runner = net.make_runner(2, 1024, torch.device("cuda"), image_hw=(96, 320))
             xyz, feat = runner(pts, img, xy)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(xyz.cpu().numpy(), g["out_xyz"])

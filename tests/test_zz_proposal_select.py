@@ -84,6 +84,12 @@ def oracle_nms_batched(rotated_default=True):
     return nms
 
 
+def _select_on_oracle(*args):
+    from backend_swap import swapped
+    with swapped(nms_batched=oracle_nms_batched()):
+        return proposal_select.select_proposals(*args)
+
+
 def oracle_nms_single(rotated):
     def nms(boxes_bev, scores, thresh):
         order = scores.sort(0, descending=True)[1]
@@ -96,7 +102,7 @@ def test_selection_equals_reference_loop_cpu(distance_based, nms_type):
     scores, props = scene_proposals(1, 3, 1500)
     rotated = nms_type == "rotate"
     for pre, post, thresh in ((900, 100, 0.7), (1200, 64, 0.85), (5000, 300, 0.5)):
-        got = proposal_select.select_proposals(scores, props, pre, post, thresh, distance_based, nms_type, nms=oracle_nms_batched())
+        got = _select_on_oracle(scores, props, pre, post, thresh, distance_based, nms_type)
         want = reference_loop(scores, props, pre, post, thresh, distance_based, oracle_nms_single(rotated))
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
         assert got[0].shape == (3, post, 7) and (got[1] > 0).any()
@@ -104,13 +110,13 @@ def test_selection_equals_reference_loop_cpu(distance_based, nms_type):
 
 def test_empty_far_band_is_served_from_the_near_band_cpu():
     scores, props = scene_proposals(2, 2, 1200, far=False)             # nothing beyond 40 m
-    got = proposal_select.select_proposals(scores, props, 600, 90, 0.8, True, "rotate", nms=oracle_nms_batched())
+    got = _select_on_oracle(scores, props, 600, 90, 0.8, True, "rotate")
     want = reference_loop(scores, props, 600, 90, 0.8, True, oracle_nms_single(True))
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
     # mixed batch: scene 0 has both bands, scene 1 only the near one
     s2, p2 = scene_proposals(3, 2, 1200)
     s2[1], p2[1] = scores[1], props[1]
-    got = proposal_select.select_proposals(s2, p2, 600, 90, 0.8, True, "normal", nms=oracle_nms_batched())
+    got = _select_on_oracle(s2, p2, 600, 90, 0.8, True, "normal")
     want = reference_loop(s2, p2, 600, 90, 0.8, True, oracle_nms_single(False))
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
 
@@ -118,12 +124,12 @@ def test_empty_far_band_is_served_from_the_near_band_cpu():
 def test_edge_cases_cpu():
     scores, props = scene_proposals(4, 2, 300)
     props[1, :, 2] = 200.0                                              # scene 1: everything outside both bands
-    got = proposal_select.select_proposals(scores, props, 100, 50, 0.7, True, "rotate", nms=oracle_nms_batched())
+    got = _select_on_oracle(scores, props, 100, 50, 0.7, True, "rotate")
     want = reference_loop(scores, props, 100, 50, 0.7, True, oracle_nms_single(True))
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
     assert not got[0][1].any() and not got[1][1].any()
     # fewer proposals than the quotas
-    got = proposal_select.select_proposals(scores[:, :40], props[:, :40], 9000, 300, 0.7, False, "rotate", nms=oracle_nms_batched())
+    got = _select_on_oracle(scores[:, :40], props[:, :40], 9000, 300, 0.7, False, "rotate")
     want = reference_loop(scores[:, :40], props[:, :40], 9000, 300, 0.7, False, oracle_nms_single(True))
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
     with pytest.raises(NotImplementedError):
