@@ -68,6 +68,22 @@ for _ in range(reps):
     ximg = torch.randn(2, 96, 320, 128, device=dev)
     conv = PackedConv3x3(torch.randn(256, 128, 3, 3, device=dev) / 34, torch.zeros(256, device=dev), stride=1)
     yimg = conv(ximg, relu=True)
+    # --- the same convolution fed by FP16 planes through TMA tensor loads (gemm_f16x3_tma_kernel), planes + fp32 out; and the
+    #     128->128 stride-2 convolution of the level above
+    from epnet_b200.gemm import Planes
+    h1 = ximg.half()
+    px = Planes(h1, ((ximg - h1.float()) * 2048.0).half())
+    conv(px, relu=True, planes_out=True)
+    xmid = torch.randn(2, 192, 640, 128, device=dev)
+    hm = xmid.half()
+    PackedConv3x3(torch.randn(128, 128, 3, 3, device=dev) / 34, None, stride=2)(Planes(hm, ((xmid - hm.float()) * 2048.0).half()), relu=False)
+    del xmid, hm
+    # --- image preparation: decoded uint8 frame -> normalised, zero-padded NHWC4 canvas; fp32 NCHW -> NHWC4
+    from epnet_b200 import image_prep
+    frame = torch.randint(0, 256, (2, 375, 1242, 3), dtype=torch.uint8, device=dev)
+    canvas = torch.empty(2, 384, 1280, 4, device=dev)
+    image_prep.normalise_pad(frame, nhwc4=canvas)
+    image_prep.nchw_to_nhwc4(torch.randn(2, 3, 384, 1280, device=dev), canvas)
     # --- the A-from-TMEM kernel (tiles of <= 64 columns): 64->64 stride-2 convolution at 384x1280, the 1x1 fusion conv shape, and a
     #     transposed convolution (128 -> 16, k = 4) writing into the 64-channel concat
     xbig = torch.randn(2, 384, 1280, 64, device=dev)
