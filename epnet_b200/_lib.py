@@ -59,6 +59,12 @@ SIGNATURES = {
     "epnet_deconv_planes_tma": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p],
     "epnet_conv3x3_nhwc_tf32x3_planes": [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,
                                          _c_void_p],
+    "epnet_tail_taps": [_c_int] * 5 + [_c_void_p] * 5,
+    "epnet_tail_plan": [_c_void_p] * 5 + [_c_int, _c_void_p],
+    "epnet_tail_scatter": [_c_int] * 4 + [_c_void_p] * 8 + [_c_int, _c_void_p],
+    "epnet_tail_blend": [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p],
+    "epnet_gemm_tf32x3_rows": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
+                               _c_void_p, _c_int, _c_void_p],
     "epnet_image_prep_u8": [_c_int] * 3 + [_c_ll, _c_ll, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "epnet_image_nchw_to_nhwc4": [_c_int] * 3 + [_c_void_p, _c_void_p, _c_void_p],
     "epnet_gemm_overflow_read": [_c_void_p, _c_void_p],

@@ -133,6 +133,13 @@ struct GemmArgs {
     // gemm_f16x3_tma_kernel, convolution mode: a CTA's 128 rows are a th x tw patch of output pixels (tw * th == 128), patches in
     // raster order over (image, patch row, patch column); 0 = rows are linear
     int tw, th, tiles_x, tiles_y;
+    // Narrow-tile kernel, sparse image tail (csrc/sparse_tail.cu): rows gathered by g_idx without offset columns (g_xyz == NULL);
+    // the number of 128-row tiles actually present is read from the device (*m_tiles_dev <= the tiles of L); the weight set of an
+    // m-tile is selected by its transposed-convolution phase: tile_phase[mt] = (Y % 16) * 16 + (X % 16) of the tile's pixels, weight
+    // n-tile ((ph >> 4) % phase_k) * phase_k + ((ph & 15) % phase_k).
+    const int *m_tiles_dev;
+    const int *tile_phase;
+    int phase_k;
 };
 
 // 16-byte global -> shared copy without register staging; bytes beyond src_bytes (0..16) are written as zero
@@ -776,7 +783,8 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
     __shared__ float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m_tiles = (a.L + kGmBM - 1) / kGmBM;  // this CTA walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one n-tile
+    int m_tiles = (a.L + kGmBM - 1) / kGmBM;  // this CTA walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one n-tile
+    if (a.m_tiles_dev) m_tiles = min(m_tiles, __ldg(a.m_tiles_dev));
     const int ntile = blockIdx.y;
     const int BN = a.BN;                           // <= 64
     const uint32_t b_bytes = (uint32_t)BN * 128;   // one plane of the W tile
@@ -849,7 +857,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
         int slot = 0;
         // grouped operand: this lane's row gets three computed columns, the sample's offset from its centre
         float goff[3] = {0.f, 0.f, 0.f};
-        if (a.g_idx) {
+        if (a.g_idx && a.g_xyz) {
             const int row = row0 + 32 * warp + lane;
             if (row < a.L) {
                 const float *pp = a.g_xyz + ((size_t)(row / a.g_rows_scene) * a.g_n + __ldg(a.g_idx + row)) * 3;
@@ -872,7 +880,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
                 v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
             }
             __syncwarp();  // the slot has been read by all lanes: refill it
-            if (a.g_idx && (kb + 1) * kGmBK > a.kcopy && kb * kGmBK < a.kcopy + 3) {  // this k-block holds offset columns
+            if (a.g_idx && a.g_xyz && (kb + 1) * kGmBK > a.kcopy && kb * kGmBK < a.kcopy + 3) {  // this k-block holds offset columns
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int col = a.kcopy + j - kb * kGmBK;
@@ -948,6 +956,11 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
             uint32_t ph = 0;
             for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
             for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                if (a.tile_phase && kb == 0) {  // this m-tile's weight set (sparse image tail)
+                    const int p16 = __ldg(a.tile_phase + mt);
+                    const int wt = ((p16 >> 4) % a.phase_k) * a.phase_k + ((p16 & 15) % a.phase_k);
+                    wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)wt * a.n_kblocks * 2 * b_bytes;
+                }
                 mbar_wait(&empty_b[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
                 bulk_g2s(b_ring + (size_t)s * 2 * b_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full_b[s]);
@@ -1143,7 +1156,7 @@ namespace epnet {
 static int gemm_launch(GemmArgs &a, cudaStream_t st)
 {
     a.n_kblocks = (a.K + kGmBK - 1) / kGmBK;
-    if (!a.g_idx) a.kcopy = a.K;
+    if (!a.g_idx || !a.g_xyz) a.kcopy = a.K;
     if (a.corr_scale == 0.f) a.corr_scale = 1.f;
     const int n_tiles = (a.N + a.BN - 1) / a.BN;
     dim3 grid((a.L + kGmBM - 1) / kGmBM, n_tiles);
@@ -1249,6 +1262,34 @@ EPNET_API int epnet_gemm_tf32x3_grouped(int scenes, int n, int m, int nsample, i
     a.relu = relu; a.pool = pool;
     a.g_idx = idx; a.g_xyz = xyz; a.g_centre = new_xyz; a.g_n = n; a.g_ns = nsample; a.g_rows_scene = m * nsample; a.kcopy = c;
     a.x_vec_ok = c > 0 && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0) && (ldf % 4 == 0);
+    return gemm_launch(a, (cudaStream_t)stream);
+}
+
+// Narrow-tile GEMM (BN <= 64) over rows GATHERED from a table: row r of the operand is x[row_idx[r]] (K floats, ldx apart); with
+// tile_phase the weight set (an n-tile of wpack, i.e. BN output columns) is chosen per 128-row tile -- the transposed-convolution
+// phase of the tile's pixels; with m_tiles_dev only the first *m_tiles_dev tiles are computed (device-side row count).  Any of the
+// three may be NULL (plain rows / one weight set / all tiles of L).  Used by the sparse evaluation of the image-fusion tail
+// (epnet_b200/sparse_tail.py; replaces the dense ConvTranspose2d + concat + 1x1 conv of /root/reference/lib/net/pointnet2_msg.py:237-243 at the
+// sampled taps only).  N <= BN: a single column tile.
+EPNET_API int epnet_gemm_tf32x3_rows(int L, int K, int N, const float *x, int ldx, const int *row_idx, const int *tile_phase, int phase_k,
+                                     const int *m_tiles_dev, const float *wpack, int BN, const float *bias, int relu, float *y, int ldy,
+                                     void *stream)
+{
+    using namespace epnet;
+    if (L < 0 || K <= 0 || N <= 0 || !x || !wpack || !y || ldx < K || ldy < N) return EPNET_ERR_BAD_ARG;
+    if (BN < 16 || BN > 64 || (BN % 16) != 0 || N > BN || (reinterpret_cast<uintptr_t>(wpack) & 15) != 0) return EPNET_ERR_BAD_ARG;
+    if (tile_phase && (phase_k < 1 || phase_k > 16 || (16 % phase_k) != 0)) return EPNET_ERR_BAD_ARG;
+    if (L == 0) return EPNET_OK;
+    GemmArgs a = {};
+    a.x = x; a.wpack = wpack; a.bias = bias; a.y = y;
+    a.L = L; a.K = K; a.N = N; a.ldx = ldx; a.ldy = ldy; a.BN = BN;
+    a.relu = relu; a.pool = 1;
+    a.x_vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+    if (row_idx) {
+        a.g_idx = row_idx; a.g_xyz = nullptr; a.g_centre = nullptr; a.g_n = 0; a.g_ns = 1; a.g_rows_scene = 0x7fffffff;
+    }
+    a.kcopy = K;
+    a.tile_phase = tile_phase; a.phase_k = phase_k; a.m_tiles_dev = m_tiles_dev;
     return gemm_launch(a, (cudaStream_t)stream);
 }
 

@@ -19,6 +19,7 @@ import torch
 
 from . import image_prep
 from . import pointnet2_cuda as pc
+from .sparse_tail import SparseImageTail
 from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
 
 
@@ -91,7 +92,7 @@ class _FusionPM:
         return self.fuse(cat, relu=True, out=out, out_cm=out_cm)
 
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True):
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True, sparse_tail=True):
         """Point-major activations + tcgen05 fp32-grade GEMMs.
         f16: the wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE), which needs activations and folded weights
         below 65504 in magnitude (they are below 10 for the published configuration).  Guarded twice: a layer whose folded
@@ -101,6 +102,10 @@ class BackboneRunner:
         tiles: gemm.tile_policy for every GEMM launch of this runner ("latency" for one batch at a time)."""
         self.tiles = tiles
         self.f16 = bool(f16)
+        # sparse_tail: evaluate the final image fusion (transposed convolutions + 1x1 conv, pointnet2_msg.py:237-243) only at the
+        # <= 4 taps of every point (sparse_tail.py) instead of over the whole up-sampled canvas; False keeps the dense form
+        self.want_sparse_tail = bool(sparse_tail)
+        self.image_hw = tuple(image_hw)
         self.overflow = OverflowFlag(device)
         self._last_stream = None
         if model.training:
@@ -226,12 +231,17 @@ class BackboneRunner:
                     img_channels.append(conv2.cout)
                     img_done.append(ev)
                 self._img_channels = img_channels
-                cat = torch.empty((B, H, W, self.deconv_cat_width), **f32)
-                col = 0
-                for i, de in enumerate(self.deconv_pm):  # each input pixel's k x k patch goes straight into its slice of the concat
-                    de(imgs[i], cat[..., col:col + de.cout])
-                    col += de.cout
-                img_fusion = self.img_fuse_pm(cat.view(-1, self.deconv_cat_width), relu=True).view(B, H, W, -1)
+                if self.sparse_tail is not None:
+                    # final image fusion at the sampled taps only; its result is the gathered feature row of every point
+                    img_fusion = torch.empty((B * N, self.img_fuse_pm.N), **f32)
+                    self.sparse_tail(imgs, xyn, img_fusion)
+                else:
+                    cat = torch.empty((B, H, W, self.deconv_cat_width), **f32)
+                    col = 0
+                    for i, de in enumerate(self.deconv_pm):  # each input pixel's k x k patch goes straight into its slice of the concat
+                        de(imgs[i], cat[..., col:col + de.cout])
+                        col += de.cout
+                    img_fusion = self.img_fuse_pm(cat.view(-1, self.deconv_cat_width), relu=True).view(B, H, W, -1)
                 img_fusion_done = torch.cuda.Event()
                 img_fusion_done.record(self.s_img)
         feats = self._point_stream_pm(main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn)
@@ -271,7 +281,15 @@ class BackboneRunner:
             wq = fc.weight.detach().flatten(1)
             # the transposed convolutions' biases pass linearly through the 1x1 fusion conv: fold them into its bias
             bq = (fc.bias.detach() if fc.bias is not None else 0) + wq @ torch.cat(biases)
-            self.img_fuse_pm = PackedLinear(*_fold_bn(wq, bq, fbn))
+            wf, bf = _fold_bn(wq, bq, fbn)
+            self.img_fuse_pm = PackedLinear(wf, bf)
+            self.sparse_tail = None
+            if self.want_sparse_tail:
+                try:
+                    self.sparse_tail = SparseImageTail(list(self.model.DeConv), wf, bf, self.B, self.N, self.image_hw, self.device,
+                                                       self.cfg.align_corners)
+                except NotImplementedError:
+                    self.sparse_tail = None  # a configuration outside its scope (kernel != stride, > 4 levels ...): dense tail
 
     def _point_stream_pm(self, main, l_xyz, l_xy, fps_done, imgs, img_done, img_fusion, img_fusion_done, xyn):
         c, B, N, dev = self.cfg, self.B, self.N, self.device
@@ -397,9 +415,12 @@ class BackboneRunner:
         feats = l_feat[0]
         if c.li_fusion:
             main.wait_event(img_fusion_done)
-            ci = img_fusion.shape[3]  # NHWC
-            g = torch.empty((B * N, ci), **f32)
-            pc.grid_gather_nhwc_pm_wrapper(B, ci, img_fusion.shape[1], img_fusion.shape[2], N, img_fusion, xyn, c.align_corners, g)
+            if self.sparse_tail is not None:
+                g = img_fusion  # (B*N, Cf): already gathered
+            else:
+                ci = img_fusion.shape[3]  # NHWC
+                g = torch.empty((B * N, ci), **f32)
+                pc.grid_gather_nhwc_pm_wrapper(B, ci, img_fusion.shape[1], img_fusion.shape[2], N, img_fusion, xyn, c.align_corners, g)
             # the last GEMM writes the interface layout (B, C, N) itself: no transposing pass
             return self.final_fusion_pm(final_cat, g, out_cm=torch.empty((B, self.final_fusion_pm.cp, N), **f32))
         return feats.view(B, N, -1).transpose(1, 2).contiguous()  # interface layout (B, C, N)

@@ -172,6 +172,29 @@ int epnet_deconv_planes_tma(int b, int h, int w, int cin, int k, int co, const v
 int epnet_conv3x3_nhwc_tf32x3_planes(int b, int h, int w, int cin, int cout, int stride, const float *x, const float *wpack, int BN,
                                      const float *bias, int relu, float *y, int ldy, void *yh1, void *yh2, int ldh, void *stream);
 
+/* ---- sparse evaluation of the final image fusion ------------------------------------------------------
+ * The reference up-samples the four image-stream maps with ConvTranspose2d (kernel == stride = 2, 4, 8, 16), concatenates them,
+ * applies a 1x1 conv + BN + ReLU to ALL 384 x 1280 pixels and bilinearly samples the result at the points
+ * (/root/reference/lib/net/pointnet2_msg.py:237-246 with Feature_Gather :107-120).  These entry points compute the fused image feature
+ * only at the <= 4 taps of every point: taps are counting-sorted by transposed-convolution phase (Y % 16, X % 16), every level is one
+ * row-gather GEMM whose 128-row tiles select their weight slice by phase, the 1x1 conv runs on the sorted rows, and a blend kernel
+ * applies the bilinear weights (same taps, weights and fma chain as epnet_grid_gather_nhwc_pm).  See epnet_b200/sparse_tail.py.
+ * epnet_tail_taps: xy (b,n,2) in [-1,1] -> tap_pix (b*n*4) = scene*H*W + y*W + x, tap_w (b*n*4), hist (256) += taps per phase.
+ * epnet_tail_plan: hist -> start (256; bins padded to 128 rows), cursor (256) = 0, tile_phase (max_tiles), *n_tiles.
+ * epnet_tail_scatter: pos_of_slot (taps) and, per level i, row_idx[i*row_stride + sorted row] = row of the level's input map.
+ * epnet_tail_blend: out (points, ldo)[0..c) = sum_t tap_w * F[pos_of_slot].
+ * epnet_gemm_tf32x3_rows: narrow-tile GEMM over rows gathered by row_idx, weight n-tile per m-tile from tile_phase, tile count from
+ * the device (any of the three may be NULL). */
+int epnet_tail_taps(int b, int n, int H, int W, int align_corners, const float *xy, int *tap_pix, float *tap_w, int *hist, void *stream);
+int epnet_tail_plan(const int *hist, int *start, int *cursor, int *tile_phase, int *n_tiles, int max_tiles, void *stream);
+int epnet_tail_scatter(int slots, int H, int W, int levels, const int *k, const int *h, const int *w, const int *tap_pix, const int *start,
+                       int *cursor, int *pos_of_slot, int *row_idx, int row_stride, void *stream);
+int epnet_tail_blend(int points, int c, const float *F, int ldf, const int *pos_of_slot, const float *tap_w, float *out, int ldo,
+                     void *stream);
+int epnet_gemm_tf32x3_rows(int L, int K, int N, const float *x, int ldx, const int *row_idx, const int *tile_phase, int phase_k,
+                           const int *m_tiles_dev, const float *wpack, int BN, const float *bias, int relu, float *y, int ldy,
+                           void *stream);
+
 /* Range guard of the FP16 operand split (no reference counterpart: pytorch_utils.py:20-32 computes in fp32).  Every GEMM
  * epilogue of this library raises a per-device flag when it writes a magnitude above 6e4 or a non-finite value -- i.e. whenever
  * a following FP16-split layer could overflow.  _read copies the flag (0/1) to host memory asynchronously on `stream` (pinned
