@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 def _dense_reference(deconvs, wf, bf, maps_nchw, xy):
     up = torch.cat([d.double()(m.double()) for d, m in zip(deconvs, maps_nchw)], dim=1)
     fused = F.relu(F.conv2d(up, wf.double()[:, :, None, None], bf.double()))
-    return F.grid_sample(fused, xy.double().unsqueeze(1), align_corners=False).squeeze(2)  # (B, Cf, N)
+    # the sampling itself in fp32, as the reference runs it (ATen grid_sampler_2d): the pixel coordinate ((x + 1) * W - 1) / 2 carries
+    # an fp32 rounding of ~W * 6e-8 pixels, i.e. up to 4e-5 in the bilinear weights at W = 1280 -- in ATen and in our kernels alike;
+    # a float64 sampler would "disagree" with both by that much (measured: 5.8e-5 of the scale at W = 1280, 1.5e-6 at W = 48)
+    return F.grid_sample(fused.float(), xy.unsqueeze(1), align_corners=False).squeeze(2).double()  # (B, Cf, N)
 
 
 @pytest.mark.parametrize("hw,cins,n", [((96, 320), (8, 16, 24, 32), 1024), ((384, 1280), (64, 128, 256, 512), 16384), ((32, 48), (64, 32), 100)])
