@@ -210,7 +210,7 @@ def measure(model, runner, dev_pool, device, world, ms_per_step=None, batches_in
         # plain, implicit-convolution and transposed-convolution launches are the same device code: gemm_tf32x3_kernel
         # (tiles wider than 64 columns) or gemm_tf32x3_ts_kernel (A operand through TMEM, tiles of <= 64 columns)
         family = ("gemm_tf32x3", "conv3x3_nhwc_tf32x3", "deconv_nhwc_tf32x3", "gemm_tf32x3_grouped", "gemm_tf32x3_cm", "conv3x3_planes_tma",
-                  "gemm_planes_tma", "deconv_planes_tma")
+                  "gemm_planes_tma", "deconv_planes_tma", "gemm_tf32x3_rows")
         e = by_name.setdefault("gemm_tf32x3_kernel" if name in family else name,
                                {"time": 0.0, "launches": 0, "bytes": 0.0, "flops": 0.0})
         e["time"] += tot / reps
@@ -234,6 +234,9 @@ def measure(model, runner, dev_pool, device, world, ms_per_step=None, batches_in
         if name == "gemm_planes_tma":  # (L, K, N, ldx, BN, relu, pool, ldy, ldh)
             e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
             e["bytes"] += 4.0 * (ints[0] * ints[1] + ints[1] * ints[2] + ints[0] // max(ints[6], 1) * ints[2]) * (cnt // reps)
+        if name == "gemm_tf32x3_rows":  # (Lmax, K, N, ldx, phase_k, BN, relu, ldy): sparse image tail; Lmax = static upper bound of the rows
+            e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
+            e["bytes"] += 4.0 * (ints[0] * ints[1] + ints[0] * ints[2]) * (cnt // reps)
         if name == "gemm_tf32x3_cm":  # (L, K, N, pts, ldx, BN, relu)
             e["flops"] += 2.0 * ints[0] * ints[1] * ints[2] * (cnt // reps)
             e["bytes"] += 4.0 * (ints[0] * ints[1] + 2 * ints[1] * ints[2] + ints[0] * ints[2]) * (cnt // reps)
