@@ -26,6 +26,7 @@
 // warp holds the whole cloud, N <= 256).  16384 < N <= 131072 spreads a scene over a thread-block cluster (DSMEM exchange of
 // the per-CTA winners); beyond that coordinates stream from L2 (fps_streaming_kernel).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace epnet {
 
@@ -601,10 +602,10 @@ static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz
 
 // 16384 < N <= 8 * 16384: a thread-block cluster of ceil(N / 16384) CTAs per scene, each with the full resident layout
 static int launch_cluster(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
-                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
+                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st, int force_csize = 0)
 {
     constexpr int NW = 16, KB = 8, KS = 4;
-    const int csize = (n + kFpsMaxResident - 1) / kFpsMaxResident;
+    const int csize = force_csize > 0 ? force_csize : (n + kFpsMaxResident - 1) / kFpsMaxResident;
     const int slice = (n + csize - 1) / csize;
     const size_t smem = (size_t)3 * NW * 32 * KB * KS * sizeof(float);
     auto kernel = fps_bucket_kernel<NW, KB, KS, true>;
@@ -649,6 +650,11 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         if (n <= 512) return launch_warp<16>(EPNET_FPS_ARGS);
         if (n <= 1024) return launch_bucket<4, 8, 1>(EPNET_FPS_ARGS);   //  32 buckets of  32
         if (n <= 4096) return launch_bucket<16, 8, 1>(EPNET_FPS_ARGS);  // 128 buckets of  32
+        {   // experiment switch: spread one scene of <= 16384 points over a cluster of 2 / 4 CTAs (DSMEM exchange per iteration)
+            static const int forced = [] { const char *e = getenv("EPNET_FPS_CLUSTER"); return e ? atoi(e) : 0; }();
+            if (forced > 1 && forced <= 8 && n >= 8192)
+                return launch_cluster(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st, forced);
+        }
         return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
         // (measured alternatives: 8 warps x 16 buckets is 27 % slower at N = 16384 -- touched buckets of one warp update
         //  serially -- and 4 warps x 8 buckets x 128 points is 25 % slower at N = 4096)
