@@ -1015,15 +1015,19 @@ struct TmaMaps {
 };
 
 __global__ void __launch_bounds__(kTmaThreads, 1)
-gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
+gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps, int m_tiles, int n_tiles)
 {
+    // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (m-tile, n-tile) grid, n fastest
+    // (neighbouring CTAs read the same activation tile: it is fetched from HBM once and served from L2).  TMEM allocation, barrier
+    // set-up and the tensor-map fetch are paid once per CTA; the shared-memory ring never drains between tiles (the producer runs
+    // ahead into the next tile while the epilogue drains the accumulator); with BN <= 128 the accumulator is double-buffered
+    // (2 x (main | correction) = 512 TMEM columns) so the epilogue of tile i overlaps the MMAs of tile i + 1.
     extern __shared__ __align__(1024) uint8_t gm_smem[];
-    __shared__ __align__(8) uint64_t full[kGmMaxStages], empty[kGmMaxStages], accum_bar;
+    __shared__ __align__(8) uint64_t full[kGmMaxStages], empty[kGmMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[256 + 32];
+    __shared__ float bias_s[2][256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntile = blockIdx.y;
     const int BN = a.BN;
     const uint32_t a_bytes = kGmBM * 128;
     const uint32_t b_bytes = (uint32_t)BN * 128;
@@ -1031,26 +1035,21 @@ gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
     const uint32_t BNP = (uint32_t)((BN + 31) & ~31);
     const uint32_t corr_off = BN <= 128 ? (uint32_t)BN : BNP;
+    const int nbuf = 4 * BNP <= 512 ? 2 : 1;        // accumulator buffers
+    const uint32_t buf_cols = 2 * BNP;              // main | correction
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2 * BNP) tmem_cols <<= 1;
-
-    // this CTA's 128 rows: a th x tw patch of output pixels (convolution) or rows [row0, row0 + 128)
-    int img = 0, oy0 = 0, ox0 = 0;
-    if (a.tw) {
-        const int per_img = a.tiles_x * a.tiles_y;
-        img = blockIdx.x / per_img;
-        const int t = blockIdx.x - img * per_img;
-        oy0 = (t / a.tiles_x) * a.th;
-        ox0 = (t - (t / a.tiles_x) * a.tiles_x) * a.tw;
-    }
-    const int row0 = blockIdx.x * kGmBM;
+    while (tmem_cols < (uint32_t)nbuf * buf_cols) tmem_cols <<= 1;
+    const int total = m_tiles * n_tiles;
 
     if (tid == 0) {
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&accum_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
         mbar_fence_init();
     }
     if (warp == 4) {
@@ -1062,27 +1061,37 @@ gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(maps.h1)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(maps.h2)) : "memory");
     }
-    for (int j = tid; j < 256 + 32; j += kTmaThreads) {
-        const int n = ntile * BN + j;
-        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_acc = tmem_base_slot;
+    const uint32_t tmem_acc0 = tmem_base_slot;
 
     if (warp < 4) {
-        // ===================== epilogue =====================
-        int row = row0 + warp * 32 + lane;
-        if (a.tw) {
-            const int r = warp * 32 + lane;
-            const int oy = oy0 + r / a.tw, ox = ox0 + (r - (r / a.tw) * a.tw);
-            row = (oy < a.Ho && ox < a.Wo) ? (img * a.Ho + oy) * a.Wo + ox : a.L;  // a.L: outside the image, nothing is stored
+        // ===================== epilogue (128 threads; named barrier 1 among them) =====================
+        for (int t = blockIdx.x, it = 0; t < total; t += gridDim.x, ++it) {
+            const int mt = t / n_tiles, ntile = t - mt * n_tiles;
+            const int buf = nbuf == 2 ? (it & 1) : 0;
+            const uint32_t par = nbuf == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+            float *bs = bias_s[it & 1];
+            for (int j = tid; j < 256 + 32; j += 128) {
+                const int n = ntile * BN + j;
+                bs[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
+            }
+            int row = mt * kGmBM + warp * 32 + lane;
+            if (a.tw) {
+                const int per_img = a.tiles_x * a.tiles_y;
+                const int img = mt / per_img, tt = mt - img * per_img;
+                const int r = warp * 32 + lane;
+                const int oy = (tt / a.tiles_x) * a.th + r / a.tw, ox = (tt - (tt / a.tiles_x) * a.tiles_x) * a.tw + (r - (r / a.tw) * a.tw);
+                row = (oy < a.Ho && ox < a.Wo) ? (img * a.Ho + oy) * a.Wo + ox : a.L;  // a.L: outside the image, nothing is stored
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // this tile's bias is in shared memory
+            mbar_wait(&acc_full[buf], par);
+            tc_fence_after();
+            gemm_epilogue(a, tmem_acc0 + (uint32_t)buf * buf_cols, corr_off, warp, lane, mt * kGmBM, ntile, bs, 0, 32, row);
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
         }
-        mbar_wait(&accum_bar, 0u);
-        tc_fence_after();
-        gemm_epilogue(a, tmem_acc, corr_off, warp, lane, row0, ntile, bias_s, 0, 32, row);
-        tc_fence_before();
     } else if (warp == 4) {
         // ===================== MMA issuer (one thread): same MMA sequence as gemm_f16x3_kernel =====================
         if (lane == 0) {
@@ -1091,53 +1100,72 @@ gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
             int s = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                mbar_wait(&full[s], ph);
+            for (int t = blockIdx.x, it = 0; t < total; t += gridDim.x, ++it) {
+                const int buf = nbuf == 2 ? (it & 1) : 0;
+                const uint32_t par = nbuf == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+                mbar_wait(&acc_empty[buf], par ^ 1u);  // the epilogue has drained this buffer (passes at once the first time round)
                 tc_fence_after();
-                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t d_a1 = umma_desc_k_sw128(base), d_a2 = umma_desc_k_sw128(base + a_bytes);
-                const uint64_t d_b1 = umma_desc_k_sw128(base + 2 * a_bytes), d_b2 = umma_desc_k_sw128(base + 2 * a_bytes + b_bytes);
+                const uint32_t tmem_acc = tmem_acc0 + (uint32_t)buf * buf_cols;
+                for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t d_a1 = umma_desc_k_sw128(base), d_a2 = umma_desc_k_sw128(base + a_bytes);
+                    const uint64_t d_b1 = umma_desc_k_sw128(base + 2 * a_bytes), d_b2 = umma_desc_k_sw128(base + 2 * a_bytes + b_bytes);
 #pragma unroll
-                for (int ks = 0; ks < kHfBK / 16; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);
-                    if (fused_b) {
-                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc2, (kb | ks) ? 1u : 0u);
-                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, 1u);
-                    } else {
-                        umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
-                        umma_f16(tmem_acc + corr_off, d_a1 + adv, d_b2 + adv, idesc, 1u);
-                        umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < kHfBK / 16; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        if (fused_b) {
+                            umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc2, (kb | ks) ? 1u : 0u);
+                            umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, 1u);
+                        } else {
+                            umma_f16(tmem_acc + corr_off, d_a2 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                            umma_f16(tmem_acc + corr_off, d_a1 + adv, d_b2 + adv, idesc, 1u);
+                            umma_f16(tmem_acc, d_a1 + adv, d_b1 + adv, idesc, (kb | ks) ? 1u : 0u);
+                        }
                     }
+                    umma_commit(&empty[s]);
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&empty[s]);
-                if (++s == a.stages) { s = 0; ph ^= 1u; }
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(&accum_bar);
         }
         __syncwarp();
     } else {
         // ===================== TMA producer (one thread): planes by tensor copies, weights by a bulk copy =====================
         if (lane == 0) {
-            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
             const int kpc = a.conv ? (1 << a.cin_shift) / kHfBK : 1;  // k-blocks per tap
             int s = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full[s], 2 * a_bytes + 2 * b_bytes);
-                uint8_t *st = smem + (size_t)s * stage_bytes;
-                if (a.conv) {
-                    const int tap = kb / kpc, c0 = (kb - tap * kpc) * kHfBK;
-                    const int ky = tap / 3, kx = tap - 3 * ky;
-                    const int cx = ox0 * a.stride + kx - 1, cy = oy0 * a.stride + ky - 1;
-                    tma_load_4d(st, maps.h1, &full[s], c0, cx, cy, img);
-                    tma_load_4d(st + a_bytes, maps.h2, &full[s], c0, cx, cy, img);
-                } else {
-                    tma_load_2d(st, maps.h1, &full[s], kb * kHfBK, row0);
-                    tma_load_2d(st + a_bytes, maps.h2, &full[s], kb * kHfBK, row0);
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int mt = t / n_tiles, ntile = t - mt * n_tiles;
+                const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
+                int img = 0, oy0 = 0, ox0 = 0;
+                if (a.tw) {
+                    const int per_img = a.tiles_x * a.tiles_y;
+                    img = mt / per_img;
+                    const int tt = mt - img * per_img;
+                    oy0 = (tt / a.tiles_x) * a.th;
+                    ox0 = (tt - (tt / a.tiles_x) * a.tiles_x) * a.tw;
                 }
-                bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full[s]);
-                if (++s == a.stages) { s = 0; ph ^= 1u; }
+                const int row0 = mt * kGmBM;
+                for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], 2 * a_bytes + 2 * b_bytes);
+                    uint8_t *st = smem + (size_t)s * stage_bytes;
+                    if (a.conv) {
+                        const int tap = kb / kpc, c0 = (kb - tap * kpc) * kHfBK;
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const int cx = ox0 * a.stride + kx - 1, cy = oy0 * a.stride + ky - 1;
+                        tma_load_4d(st, maps.h1, &full[s], c0, cx, cy, img);
+                        tma_load_4d(st + a_bytes, maps.h2, &full[s], c0, cx, cy, img);
+                    } else {
+                        tma_load_2d(st, maps.h1, &full[s], kb * kHfBK, row0);
+                        tma_load_2d(st + a_bytes, maps.h2, &full[s], kb * kHfBK, row0);
+                    }
+                    bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full[s]);
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
         __syncwarp();
@@ -1146,7 +1174,7 @@ gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps)
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc0), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -1441,27 +1469,28 @@ static int gemm_launch_tma(GemmArgs &a, const void *xh1, const void *xh2, int ld
         }
         if (r != CUDA_SUCCESS) return EPNET_ERR_BAD_ARG;
     }
-    dim3 grid;
+    int m_tiles;
     if (a.conv) {
         a.tw = kTmaTileW; a.th = kTmaTileH;
         a.tiles_x = (a.Wo + kTmaTileW - 1) / kTmaTileW;
         a.tiles_y = (a.Ho + kTmaTileH - 1) / kTmaTileH;
-        grid = dim3((unsigned)(batch * a.tiles_x * a.tiles_y), (unsigned)n_tiles);
+        m_tiles = batch * a.tiles_x * a.tiles_y;
     } else {
-        grid = dim3((unsigned)((a.L + kGmBM - 1) / kGmBM), (unsigned)n_tiles);
+        m_tiles = (a.L + kGmBM - 1) / kGmBM;
     }
+    const long long total_tiles = (long long)m_tiles * n_tiles;
+    dim3 grid((unsigned)(total_tiles < kSmCount ? total_tiles : kSmCount));  // persistent: one CTA per SM
     const size_t sb = 2 * (size_t)kGmBM * 128 + 2 * (size_t)a.BN * 128;
     int st_ = (int)((200 * 1024) / sb);
     if (st_ > kGmMaxStages) st_ = kGmMaxStages;
-    if (st_ > a.n_kblocks) st_ = a.n_kblocks;
-    if (st_ < 1) st_ = 1;
+    if (st_ < 1) st_ = 1;  // the ring runs across tiles: keep every stage even when a tile has fewer k-blocks
     a.stages = st_;
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)gemm_f16x3_tma_kernel);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute((const void *)gemm_f16x3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return (int)e;
-    gemm_f16x3_tma_kernel<<<grid, kTmaThreads, sb * st_ + 1024, st>>>(a, maps);
+    gemm_f16x3_tma_kernel<<<grid, kTmaThreads, sb * st_ + 1024, st>>>(a, maps, m_tiles, n_tiles);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 

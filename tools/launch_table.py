@@ -14,7 +14,9 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
 model = bench.build_model(dev)
-runner = model.make_runner(2, 16384, dev, use_graph=False)
+from epnet_b200.runner import BackboneRunner  # noqa: E402
+tiles = sys.argv[2] if len(sys.argv) > 2 else "latency"  # "throughput" = the tile policy of the pipelined (benchmarked) runners
+runner = BackboneRunner(model, 2, 16384, dev, use_graph=False, tiles=tiles)
 pool = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_pool(2, 1000)]
 for i in range(3):
     runner.eager(pool[i % 2]["points"], pool[i % 2]["image"], pool[i % 2]["xy"], single_stream=True)
