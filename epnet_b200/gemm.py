@@ -112,10 +112,11 @@ class Planes:
 
 def tma_bn(n, rows):
     """column tile of the TMA-fed FP16-split kernel: the whole layer up to 256 columns; 128 when 256-column tiles would leave most SMs idle"""
-    if n <= 256:
+    cap = int(_os.environ.get("EPNET_TMA_BN_MAX", "128"))  # 128: every tile double-buffers its accumulator (epilogue overlaps the MMAs)
+    if n <= cap:
         return (n + 15) // 16 * 16
-    bn = 256
-    if ((rows + 127) // 128) * ((n + 255) // 256) < 100 and n % 128 == 0:
+    bn = cap
+    if cap == 256 and ((rows + 127) // 128) * ((n + 255) // 256) < 100 and n % 128 == 0:
         bn = 128
     return bn
 
