@@ -12,7 +12,6 @@
 // (replaces a zero-fill + strided copy of torch elementwise kernels in front of every forward).
 // Both are pure streaming kernels: HBM/L2 bandwidth bound (3 or 12 bytes in, 16 [+12] bytes out per pixel).
 #include "common.cuh"
-#include <cuda_fp16.h>
 
 namespace epnet {
 
@@ -58,78 +57,6 @@ image_nchw_to_nhwc4_kernel(int b, int H, int W, const float *__restrict__ src, f
     }
 }
 
-
-// ---- im2col form for the first convolution ------------------------------------------------------------------------------------
-// The first 3x3 convolution has 3 input channels: as an implicit GEMM its A operand is 9 taps x 4 (padded) channels = 36 values per
-// output pixel, gathered 16 bytes at a time -- measured instruction-bound (179 us for 4.5 GFLOP).  Here the preparation kernel
-// writes that operand itself, once, already split into the two FP16 planes of the FP16 split (h1 = fp16(x), h2 = fp16((x - h1) * 2^11)):
-// cols[(b, y, x)][k], k = (ky * 3 + kx) * 4 + c for the pixel (y + ky - 1, x + kx - 1) (zero outside the canvas; c = 3 and k >= 36 are zero),
-// 64 halfs per pixel and plane.  The convolution is then ONE k-block of the TMA-fed GEMM (epnet_gemm_planes_tma, K = 36 padded to 64).
-__device__ __forceinline__ uint32_t split_pack(float x)  // low half h1, high half h2
-{
-    const __half h1 = __float2half_rn(x);
-    const __half h2 = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(h1)), 2048.0f));
-    return (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h2) << 16);
-}
-
-template <bool kFromU8>
-__global__ void __launch_bounds__(256)
-image_cols_kernel(int b, int h_in, int w_in, long long pitch_in, long long scene_in, const int *sizes, int H, int W, double m0, double m1,
-                  double m2, double s0, double s1, double s2, const uint8_t *__restrict__ src_u8, const float *__restrict__ src_f32,
-                  uint4 *__restrict__ cols_h1, uint4 *__restrict__ cols_h2)
-{
-    __shared__ uint32_t lut[3][256];  // (h1 | h2 << 16) of every possible normalised value
-    if (kFromU8) {
-        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-            const int c = i >> 8, v = i & 255;
-            const double mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-            lut[c][v] = split_pack((float)(((double)v / 255.0 - mean) / sd));
-        }
-        __syncthreads();
-    }
-    const long long total = (long long)b * H * W;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(p % W);
-        const long long t = p / W;
-        const int y = (int)(t % H), s = (int)(t / H);
-        int hs = H, ws = W;
-        if (kFromU8) {
-            hs = sizes ? min(__ldg(sizes + 2 * s), h_in) : h_in;
-            ws = sizes ? min(__ldg(sizes + 2 * s + 1), w_in) : w_in;
-        }
-        uint32_t v[36];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-            const bool in = yy >= 0 && yy < hs && xx >= 0 && xx < ws;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint32_t q = 0u;
-                if (in) {
-                    if (kFromU8) q = lut[c][__ldg(src_u8 + (size_t)s * scene_in + (size_t)yy * pitch_in + (size_t)xx * 3 + c)];
-                    else q = split_pack(__ldg(src_f32 + (((size_t)s * 3 + c) * H + yy) * W + xx));
-                }
-                v[tap * 4 + c] = q;
-            }
-            v[tap * 4 + 3] = 0u;
-        }
-        uint4 *d1 = cols_h1 + p * 8, *d2 = cols_h2 + p * 8;  // 64 halfs = 8 x 16 bytes per pixel and plane
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t a1[4], a2[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k0 = j * 8 + 2 * e;
-                const uint32_t qa = k0 < 36 ? v[k0 < 36 ? k0 : 0] : 0u, qb = k0 + 1 < 36 ? v[k0 + 1 < 36 ? k0 + 1 : 0] : 0u;
-                a1[e] = (qa & 0xffffu) | (qb << 16);
-                a2[e] = (qa >> 16) | (qb & 0xffff0000u);
-            }
-            __stcs(d1 + j, make_uint4(a1[0], a1[1], a1[2], a1[3]));
-            __stcs(d2 + j, make_uint4(a2[0], a2[1], a2[2], a2[3]));
-        }
-    }
-}
-
 }  // namespace epnet
 
 // src: b decoded images, uint8 RGB interleaved, scene s at src + s*scene_stride, row y at + y*pitch (bytes), h_in x w_in pixels
@@ -160,39 +87,5 @@ EPNET_API int epnet_image_nchw_to_nhwc4(int b, int H, int W, const float *src, f
     const long long total = (long long)b * H * W;
     const int blocks = (int)min((long long)kSmCount * 8, (total + 255) / 256);
     image_nchw_to_nhwc4_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, H, W, src, reinterpret_cast<float4 *>(dst));
-    EPNET_RETURN_LAUNCH_STATUS();
-}
-
-// The decoded uint8 frames (arguments as epnet_image_prep_u8) -> the im2col operand of the first 3x3 convolution as FP16 planes:
-// cols_h1, cols_h2 (b*H*W, 64) halfs, k = (ky*3 + kx)*4 + c, see image_cols_kernel.  16-byte aligned.
-EPNET_API int epnet_image_prep_u8_cols(int b, int h_in, int w_in, long long pitch, long long scene_stride, const unsigned char *src,
-                                       const int *sizes, int H, int W, const double *mean, const double *std, void *cols_h1, void *cols_h2,
-                                       void *stream)
-{
-    using namespace epnet;
-    if (b < 0 || h_in <= 0 || w_in <= 0 || H <= 0 || W <= 0 || !src || !mean || !std || !cols_h1 || !cols_h2) return EPNET_ERR_BAD_ARG;
-    if (pitch < 3ll * w_in || scene_stride < pitch * h_in || h_in > H || w_in > W) return EPNET_ERR_BAD_ARG;
-    if (std[0] == 0.0 || std[1] == 0.0 || std[2] == 0.0) return EPNET_ERR_BAD_ARG;
-    if ((reinterpret_cast<uintptr_t>(cols_h1) | reinterpret_cast<uintptr_t>(cols_h2)) & 15) return EPNET_ERR_BAD_ARG;
-    if (b == 0) return EPNET_OK;
-    const long long total = (long long)b * H * W;
-    const int blocks = (int)min((long long)kSmCount * 16, (total + 255) / 256);
-    image_cols_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(b, h_in, w_in, pitch, scene_stride, sizes, H, W, mean[0], mean[1], mean[2],
-                                                                     std[0], std[1], std[2], src, nullptr, reinterpret_cast<uint4 *>(cols_h1),
-                                                                     reinterpret_cast<uint4 *>(cols_h2));
-    EPNET_RETURN_LAUNCH_STATUS();
-}
-
-// The reference's fp32 (b,3,H,W) image tensor -> the same im2col planes.
-EPNET_API int epnet_image_nchw_to_cols(int b, int H, int W, const float *src, void *cols_h1, void *cols_h2, void *stream)
-{
-    using namespace epnet;
-    if (b < 0 || H <= 0 || W <= 0 || !src || !cols_h1 || !cols_h2) return EPNET_ERR_BAD_ARG;
-    if ((reinterpret_cast<uintptr_t>(cols_h1) | reinterpret_cast<uintptr_t>(cols_h2)) & 15) return EPNET_ERR_BAD_ARG;
-    if (b == 0) return EPNET_OK;
-    const long long total = (long long)b * H * W;
-    const int blocks = (int)min((long long)kSmCount * 16, (total + 255) / 256);
-    image_cols_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(b, H, W, 0, 0, nullptr, H, W, 0, 0, 0, 1, 1, 1, nullptr, src,
-                                                                      reinterpret_cast<uint4 *>(cols_h1), reinterpret_cast<uint4 *>(cols_h2));
     EPNET_RETURN_LAUNCH_STATUS();
 }

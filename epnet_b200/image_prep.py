@@ -52,23 +52,3 @@ def nchw_to_nhwc4(image, out=None):
         out = torch.empty((b, H, W, 4), dtype=torch.float32, device=image.device)
     pc._call("image_nchw_to_nhwc4", LIB.epnet_image_nchw_to_nhwc4, image, b, H, W, pc._f(image, "image"), pc._f(out, "out"))
     return out
-
-
-def first_conv_cols(image, cols, sizes=None, out_hw=CANVAS_HW, mean=MEAN, std=STD):
-    """The im2col operand of the first 3x3 convolution (3 input channels) as FP16 planes, straight from the image: `image` is the decoded
-    uint8 frame (B,h,w,3) or the reference's fp32 (B,3,H,W) tensor (device); cols = gemm.Planes of shape (B*H*W, 64), k = (ky*3+kx)*4 + c."""
-    H, W = out_hw
-    if image.dtype == torch.uint8:
-        b, h, w, _ = image.shape
-        if image.stride(-1) != 1 or image.stride(-2) != 3 or h > H or w > W or not image.is_cuda:
-            raise ValueError("uint8 frame must be a CUDA (B,h,w,3) tensor of interleaved RGB bytes inside the canvas")
-        assert cols.shape == (b * H * W, 64) and cols.h1.is_contiguous() and cols.h2.is_contiguous()
-        pc._call("image_prep_u8_cols", LIB.epnet_image_prep_u8_cols, image, b, h, w, image.stride(1), image.stride(0), image.data_ptr(),
-                 None if sizes is None else pc._i(sizes, "sizes"), H, W, _dbl3(mean), _dbl3(std), cols.h1.data_ptr(), cols.h2.data_ptr())
-    else:
-        b = image.shape[0]
-        if image.shape[1:] != (3, H, W):
-            raise ValueError("fp32 image must be (B,3,%d,%d)" % (H, W))
-        assert cols.shape == (b * H * W, 64) and cols.h1.is_contiguous() and cols.h2.is_contiguous()
-        pc._call("image_nchw_to_cols", LIB.epnet_image_nchw_to_cols, image, b, H, W, pc._f(image, "image"), cols.h1.data_ptr(), cols.h2.data_ptr())
-    return cols

@@ -20,8 +20,7 @@ import torch
 from . import image_prep
 from . import pointnet2_cuda as pc
 from .sparse_tail import SparseImageTail
-from . import gemm as _gemm
-from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, Planes, f16_split, grouped_first_layer, tile_policy
+from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
 
 
 class _nvtx:
@@ -122,8 +121,7 @@ class BackboneRunner:
         # the graph's image input: the NHWC canvas, channels padded to 4, that the first convolution reads.  It is produced in
         # front of the replay by one kernel from whatever the caller holds (image_prep.py): the decoded uint8 image, or the
         # reference's fp32 (B,3,H,W) tensor.  Staging buffers for host inputs are allocated on first use.
-        self.image4 = None   # allocated in _build_pm: the NHWC4 canvas, or (planes chain) self.image_cols, the first convolution's im2col planes
-        self.image_cols = None
+        self.image4 = torch.zeros(batch, H, W, 4, **f32)
         self._stage_f32 = None
         self._stage_u8 = None
         self.xy = torch.zeros(batch, npoints, 2, **f32)
@@ -195,7 +193,7 @@ class BackboneRunner:
             # NHWC activations; 3x3 convolutions, transposed convolutions and the 1x1 fusion conv on the tcgen05 3xTF32 GEMM
             with torch.cuda.stream(self.s_img), _nvtx("image_stream"):
                 self.s_img.wait_event(ready)
-                H, W = self.image_hw
+                H, W = self.image4.shape[1], self.image4.shape[2]
                 x = self.image4
                 def run_conv(conv, inp, relu):
                     # the next convolution wants a power-of-two channel count: pad the buffer (zeros) when Cout is not one
@@ -210,15 +208,16 @@ class BackboneRunner:
                     return buf
 
                 img_channels = []
-                chain = self.chain
+                # Planes chain: every convolution after the first reads its input as the two FP16 planes the previous one's epilogue
+                # wrote, through TMA tensor loads (gemm.Planes, csrc gemm_f16x3_tma_kernel): each activation is split once, by its
+                # producer, instead of once per tap and column tile by the consumers' SIMT producer warps.  Needs the FP16 split
+                # to be on (range guard: overflowed()) and channel counts that are multiples of 64 (a k-block = one tap x 64 channels).
+                chain = self.f16 and all(c1.cout % 64 == 0 and c2.planes_capable() for c1, c2 in self.img_blocks_pm) and \
+                    all(c1.planes_capable() for c1, _ in self.img_blocks_pm[1:])
                 planes = None
                 for bi, (conv1, conv2) in enumerate(self.img_blocks_pm):
                     if chain:
-                        if bi == 0:  # one k-block GEMM over the im2col planes; its output planes are the (B, H, W, Cout) image
-                            _, flat = conv1.lin.from_planes(self.image_cols, relu=True, planes_out=True, f32_out=False)
-                            mid = Planes(flat.h1.view(B, H, W, conv1.cout), flat.h2.view(B, H, W, conv1.cout))
-                        else:
-                            _, mid = conv1(planes, relu=True, planes_out=True, f32_out=False)
+                        _, mid = conv1(x if bi == 0 else planes, relu=True, planes_out=True, f32_out=False)
                         last = bi + 1 == len(self.img_blocks_pm)
                         if last:
                             x = conv2(mid, relu=False)
@@ -271,22 +270,6 @@ class BackboneRunner:
             # image stream on the tcgen05 GEMM, NHWC
             self.img_blocks_pm = [(PackedConv3x3(w1, b1, stride=stride[0]), PackedConv3x3(conv2.weight, None, stride=conv2.stride[0]))
                                   for (w1, b1, stride, conv2) in self.img_blocks]
-            # Planes chain: every convolution reads its input as the two FP16 planes the previous one's epilogue wrote, through TMA
-            # tensor loads (gemm.Planes, csrc gemm_f16x3_tma_kernel): each activation is split once, by its producer, instead of once
-            # per tap and column tile by the consumers' SIMT producer warps.  The FIRST convolution (3 input channels) reads the
-            # im2col planes the image-preparation kernel writes (image_prep.first_conv_cols): one k-block of the same kernel.
-            # Needs the FP16 split (range guard: overflowed()), a 3-channel stride-1 first convolution and channel counts that are
-            # multiples of 64 (a k-block = one tap x 64 channels); anything else takes the fp32 NHWC path below.
-            with f16_split(self.f16):
-                first = self.img_blocks_pm[0][0]
-                self.chain = (_gemm.F16_WIDE and first.cin == 3 and first.stride == 1 and first.lin.f16_ok
-                              and all(c1.cout % 64 == 0 and c2.planes_capable() for c1, c2 in self.img_blocks_pm)
-                              and all(c1.planes_capable() for c1, _ in self.img_blocks_pm[1:]))
-            H, W = self.image_hw
-            if self.chain:
-                self.image_cols = Planes.empty((self.B * H * W, 64), self.device)
-            else:
-                self.image4 = torch.zeros(self.B, H, W, 4, dtype=torch.float32, device=self.device)
             self.deconv_pm, biases = [], []
             for de in self.model.DeConv:  # ConvTranspose2d weight: (Cin, Cout, k, k), kernel == stride
                 k, co = de.kernel_size[0], de.out_channels
@@ -470,20 +453,15 @@ class BackboneRunner:
                 image = self._stage_u8
             if sizes is not None and not sizes.is_cuda:
                 sizes = sizes.to(self.device, non_blocking=True)
-            if self.chain:
-                image_prep.first_conv_cols(image, self.image_cols, sizes, out_hw=self.image_hw)
-            else:
-                image_prep.normalise_pad(image, sizes, out_hw=self.image_hw, nhwc4=self.image4)
+            image_prep.normalise_pad(image, sizes, out_hw=tuple(self.image4.shape[1:3]), nhwc4=self.image4)
             return
         if not image.is_cuda or not image.is_contiguous():
             if self._stage_f32 is None:
-                self._stage_f32 = torch.empty(self.B, 3, self.image_hw[0], self.image_hw[1], dtype=torch.float32, device=self.device)
+                self._stage_f32 = torch.empty(self.image4.shape[0], 3, self.image4.shape[1], self.image4.shape[2], dtype=torch.float32,
+                                              device=self.device)
             self._stage_f32.copy_(image, non_blocking=True)
             image = self._stage_f32
-        if self.chain:
-            image_prep.first_conv_cols(image, self.image_cols, out_hw=self.image_hw)
-        else:
-            image_prep.nchw_to_nhwc4(image, self.image4)
+        image_prep.nchw_to_nhwc4(image, self.image4)
 
     def __call__(self, points, image, xy, sizes=None):
         """points (B,N,3); image: the reference's fp32 (B,3,H,W) tensor, or the decoded uint8 RGB image (B,h,w,3) with optional

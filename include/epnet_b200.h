@@ -214,13 +214,6 @@ int epnet_image_prep_u8(int b, int h_in, int w_in, long long pitch, long long sc
                         int H, int W, const double *mean, const double *std, float *nhwc4, float *nchw, void *stream);
 /* (b,3,H,W) fp32 -> (b,H,W,4) fp32, channel 3 = 0: the layout change in front of the first convolution, one pass. */
 int epnet_image_nchw_to_nhwc4(int b, int H, int W, const float *src, float *dst, void *stream);
-/* The same two sources -> the im2col operand of the FIRST 3x3 convolution (Img_Block[0].conv1, /root/reference/lib/net/pointnet2_msg.py:17-24; 3 input
- * channels), already split into the FP16 planes a *_planes_tma layer reads: cols_h1, cols_h2 (b*H*W, 64) halfs with
- * k = (ky*3 + kx)*4 + c holding pixel (y + ky - 1, x + kx - 1), zero outside the canvas, for c = 3 and for k >= 36.  The convolution is then
- * epnet_gemm_planes_tma with K = 36. */
-int epnet_image_prep_u8_cols(int b, int h_in, int w_in, long long pitch, long long scene_stride, const unsigned char *src, const int *sizes,
-                             int H, int W, const double *mean, const double *std, void *cols_h1, void *cols_h2, void *stream);
-int epnet_image_nchw_to_cols(int b, int H, int W, const float *src, void *cols_h1, void *cols_h2, void *stream);
 
 /* First shared-MLP layer of a set-abstraction scale with QueryAndGroup fused into the operand load (pointnet2_utils.py:241-264 +
  * pointnet2_modules.py:47-52): GEMM row (scene, centre p, sample s) = [feats[scene, idx[scene,p,s], 0..c) | xyz[scene, idx] -

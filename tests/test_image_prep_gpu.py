@@ -85,30 +85,3 @@ def test_backbone_from_decoded_image_equals_backbone_from_prepared_tensor(pipeli
         _, f_m1 = model(d["points"], d["image"], d["xy"].clone())
         _, f_m2 = model(d["points"], d["image_u8"], d["xy"].clone())
     assert torch.equal(f_m1, f_m2)
-
-
-def test_first_conv_cols_from_both_sources_and_conv_parity():
-    """im2col planes of the first convolution: uint8 source == fp32 source bit for bit; the one-k-block GEMM over them == the 3x3
-    convolution in float64 (borders, ragged frame)."""
-    import torch.nn.functional as F
-    from epnet_b200 import image_prep
-    from epnet_b200.gemm import PackedConv3x3, Planes
-    rng = np.random.RandomState(3)
-    H, W = 64, 96
-    img = rng.randint(0, 256, size=(2, 61, 90, 3)).astype(np.uint8)
-    dev = torch.from_numpy(img).cuda()
-    fp32 = image_prep.normalise_pad(dev, out_hw=(H, W))                      # (2,3,H,W)
-    a, b = Planes.empty((2 * H * W, 64), "cuda"), Planes.empty((2 * H * W, 64), "cuda")
-    image_prep.first_conv_cols(dev, a, out_hw=(H, W))
-    image_prep.first_conv_cols(fp32, b, out_hw=(H, W))
-    torch.cuda.synchronize()
-    assert torch.equal(a.h1, b.h1) and torch.equal(a.h2, b.h2)
-    assert float(a.h1[:, 36:].abs().max()) == 0.0 and float(a.h1.view(-1, 16, 4)[:, :9, 3].abs().max()) == 0.0
-    g = torch.Generator().manual_seed(0)
-    w = (torch.randn(64, 3, 3, 3, generator=g) / 5).cuda()
-    bias = torch.randn(64, generator=g).cuda()
-    conv = PackedConv3x3(w, bias, stride=1)
-    y = conv.lin.from_planes(a, relu=True).view(2, H, W, 64)
-    want = F.relu(F.conv2d(fp32.double(), w.double(), bias.double(), padding=1)).permute(0, 2, 3, 1)
-    err = (y.double() - want).abs().max().item() / want.abs().max().item()
-    assert err <= 4e-6, err
