@@ -369,29 +369,47 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
                 }
             }
         } else {
-            // max over `pool` consecutive rows (= lanes): order-preserving float->uint map, then an xor-butterfly inside
-            // aligned groups of `pool` lanes; each step runs over all 32 columns (independent shuffles in flight)
+            // max over `pool` consecutive rows (= lanes).  Values are compared as unsigned words: after ReLU they are non-negative floats
+            // (whose bit patterns order like the values; rows past the end contribute 0), otherwise through the order-preserving
+            // float -> uint map.  Reduction by recursive halving inside aligned groups of `pool` lanes: at step d a lane keeps one half
+            // of its live columns and hands the other half to lane ^ d, so 32 columns cost 16 + 8 + ... shuffles (31 for pool = 32)
+            // instead of 32 per step, and each lane ends up owning 32 / pool distinct columns of its group's result.
+            const bool mapped = !a.relu;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const uint32_t u = row < a.L ? v[j] : 0xff800000u;  // -inf for rows past the end
-                v[j] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                uint32_t u = v[j];
+                if (mapped) {
+                    u = row < a.L ? u : 0xff800000u;  // -inf for rows past the end
+                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                } else {
+                    u = row < a.L ? u : 0u;
+                }
+                v[j] = u;
             }
+            int col_base = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            for (int k = 0; k < 5; ++k) {
+                const int d = 1 << k, half = 16 >> k;  // live columns before this step: 2 * half
                 if (d < pool) {  // warp-uniform
+                    const bool upper = (lane & d) != 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], d));
+                    for (int i = 0; i < half; ++i) {
+                        const uint32_t mine = upper ? v[i + half] : v[i];
+                        const uint32_t give = upper ? v[i] : v[i + half];
+                        v[i] = max(mine, __shfl_xor_sync(0xffffffffu, give, d));
+                    }
+                    col_base += upper ? half : 0;
                 }
             }
-            // every lane of a group now holds the group's maxima; lane t of the group stores columns j == t (mod pool)
+            // live: v[0 .. 32/pool), columns col_base + i of this lane's group
             if (row < a.L) {
-                float *dst = a.y + (size_t)(row / pool) * a.ldy + n0;
-                const int t = lane % pool;
+                float *dst = a.y + (size_t)(row / pool) * a.ldy + n0 + col_base;
+                const int live = 32 / pool;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((j % pool) == t && j < ncols && n0 + j < a.N) {
-                        const uint32_t u = v[j];
-                        dst[j] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+                for (int i = 0; i < 16; ++i) {
+                    if (i < live && col_base + i < ncols && n0 + col_base + i < a.N) {
+                        const uint32_t u = v[i];
+                        dst[i] = __uint_as_float(mapped ? ((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u) : u);
                     }
                 }
             }
