@@ -307,11 +307,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
         const int ncols = min(32, BN - c0);
         const int n0 = ntile * BN + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float f = __fmaf_rn(__uint_as_float(w[j]), a.corr_scale, __uint_as_float(v[j])) + bias_s[c0 + j];  // scale 1: an exact add
-            if (a.relu) f = fmaxf(f, 0.f);
-            amax = fmaxf(amax, fabsf(f));  // padding rows/columns hold bias-only values: harmless
-            v[j] = __float_as_uint(f);
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + c0 + j4);  // c0 is a multiple of 32, bias_s 16-byte aligned
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 + e;
+                float f = __fmaf_rn(__uint_as_float(w[j]), a.corr_scale, __uint_as_float(v[j])) + bb[e];  // scale 1: an exact add
+                if (a.relu) f = fmaxf(f, 0.f);
+                amax = fmaxf(amax, fabsf(f));  // padding rows/columns hold bias-only values: harmless
+                v[j] = __float_as_uint(f);
+            }
         }
         if (a.tr) {
             if (row < a.L) {
@@ -344,12 +350,13 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
                     if (j < ncols) {
                         uint32_t q1[4], q2[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            __half a1, a2, b1, b2;
-                            split_f16(__uint_as_float(v[j + 2 * e]), a1, a2);
-                            split_f16(__uint_as_float(v[j + 2 * e + 1]), b1, b2);
-                            q1[e] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
-                            q2[e] = (uint32_t)__half_as_ushort(a2) | ((uint32_t)__half_as_ushort(b2) << 16);
+                        for (int e = 0; e < 4; ++e) {  // two values per packed conversion; (x - h1) and the scaling by 2^11 are exact in fp32
+                            const float x0 = __uint_as_float(v[j + 2 * e]), x1 = __uint_as_float(v[j + 2 * e + 1]);
+                            const __half2 p1 = __floats2half2_rn(x0, x1);
+                            const float2 f1 = __half22float2(p1);
+                            const __half2 p2 = __floats2half2_rn(__fmul_rn(__fsub_rn(x0, f1.x), 2048.0f), __fmul_rn(__fsub_rn(x1, f1.y), 2048.0f));
+                            q1[e] = *reinterpret_cast<const uint32_t *>(&p1);
+                            q2[e] = *reinterpret_cast<const uint32_t *>(&p2);
                         }
                         *reinterpret_cast<uint4 *>(d1 + j) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
                         *reinterpret_cast<uint4 *>(d2 + j) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
@@ -424,7 +431,7 @@ gemm_tf32x3_kernel(const GemmArgs a)
     extern __shared__ __align__(1024) uint8_t gm_smem[];
     __shared__ __align__(8) uint64_t full_a[kGmMaxStages], full_b[kGmMaxStages], empty[kGmMaxStages], accum_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[256 + 32];
+    __shared__ __align__(16) float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kGmBM;
@@ -605,7 +612,7 @@ gemm_f16x3_kernel(const GemmArgs a)
     extern __shared__ __align__(1024) uint8_t gm_smem[];
     __shared__ __align__(8) uint64_t full_a[kGmMaxStages], full_b[kGmMaxStages], empty[kGmMaxStages], accum_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[256 + 32];
+    __shared__ __align__(16) float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kGmBM;
@@ -798,7 +805,7 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
     __shared__ __align__(8) uint64_t full_a[kTsMaxAStages], empty_a[kTsMaxAStages], full_b[kTsMaxBStages], empty_b[kTsMaxBStages], accum_bar,
         acc_empty;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[256 + 32];
+    __shared__ __align__(16) float bias_s[256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int m_tiles = (a.L + kGmBM - 1) / kGmBM;  // this CTA walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of one n-tile
@@ -1043,7 +1050,7 @@ gemm_f16x3_tma_kernel(const GemmArgs a, const __grid_constant__ TmaMaps maps, in
     extern __shared__ __align__(1024) uint8_t gm_smem[];
     __shared__ __align__(8) uint64_t full[kGmMaxStages], empty[kGmMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float bias_s[2][256 + 32];
+    __shared__ __align__(16) float bias_s[2][256 + 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BN = a.BN;
