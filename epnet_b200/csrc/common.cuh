@@ -68,20 +68,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Keep this the bare try_wait loop: adding a poll counter (to trap on a protocol error) measured ~50 ns slower per wait on the
-// GEMM's MMA-issue critical path, in PTX or C++ alike.
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the hint expires)
+// instead of re-issuing the poll.  Without the hint the bare try_wait loop of the single-lane MMA / loader warps and of the
+// producer warps accounted for ~40 % of all issued instructions of the narrow-tile GEMM (ncu source page, r02k), stealing issue slots
+// from the epilogue warps on the same schedulers.  (A software poll COUNTER, to trap on protocol errors, measured ~50 ns slower per
+// wait on the MMA-issue critical path in round 1 and is still not used.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 // dst/src 16-byte aligned, bytes a multiple of 16.
