@@ -9,7 +9,7 @@ python - <<PY
 import json
 try:
     o=json.load(open("gpurun_out/${T}_bench.json"))
-    print({k:o.get(k) for k in ("value","ms_per_step","e2e","e2e_uint8_image","one_batch_at_a_time")})
+    print({k:o.get(k) for k in ("value","ms_per_step","e2e","e2e_fp32_image","one_batch_at_a_time")})
     print({k:o["roofline"].get(k) for k in ("achieved","frac","tensor_pipe_frac","isolated")})
     for k in o["kernel_breakdown"][:12]: print(k)
 except Exception as e: print("no bench line", e); print(open("gpurun_out/${T}_bench.err").read()[-2000:])
