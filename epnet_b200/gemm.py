@@ -242,7 +242,7 @@ class PackedLinear:
 def grouped_first_layer(lin, xyz, new_xyz, feats_pm, idx, relu=True, pool=1, out=None):
     """lin(group(xyz, new_xyz, feats, idx)) without the grouped tensor: lin = PackedLinear over [features (C) | offsets (3)];
     xyz (B,n,3), new_xyz (B,m,3), feats_pm (B,n,C) point-major or None, idx (B,m,ns) -> (B*m*ns / pool, N).
-    Returns None when this layer cannot take the fused path (column tile wider than 64): the caller groups explicitly."""
+    Every width takes the fused path (tiles wider than 64 columns are cut into 64-column tiles of the narrow kernel)."""
     B, n = xyz.shape[0], xyz.shape[1]
     m, ns = idx.shape[1], idx.shape[2]
     c = 0 if feats_pm is None else feats_pm.shape[-1]
@@ -250,7 +250,11 @@ def grouped_first_layer(lin, xyz, new_xyz, feats_pm, idx, relu=True, pool=1, out
     rows = B * m * ns
     bn, wpack = lin.for_rows(rows)
     if bn > 64:
-        return None
+        # the grouped operand exists on the narrow-tile kernel only (A through TMEM): wider layers (the 515 -> 256 first layers of the
+        # last set-abstraction level) run as 64-column tiles of it, each gathering its rows again -- a few thousand rows, cheaper than
+        # materialising QueryAndGroup's tensor and reading it back
+        bn = 64
+        wpack = lin._pack(bn)
     if out is None:
         out = torch.empty((rows // pool, lin.N), dtype=torch.float32, device=xyz.device)
     pc._call("gemm_tf32x3_grouped", LIB.epnet_gemm_tf32x3_grouped, xyz, B, n, m, ns, c, None if feats_pm is None else feats_pm.data_ptr(),

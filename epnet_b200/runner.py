@@ -365,7 +365,7 @@ class BackboneRunner:
                     # first layer: the grouped rows go from the feature table straight into the tensor-core operand
                     x = grouped_first_layer(lins[0], xyz, new_xyz, fpm, bidx, relu=True) if len(lins) > 1 else None
                     rest = lins[1:-1]
-                    if x is None:  # column tile wider than 64 (or a one-layer MLP): materialise the grouped rows
+                    if x is None:  # a one-layer MLP (its only layer carries the pooled epilogue): materialise the grouped rows
                         kp = (cin + 3 + 3) // 4 * 4
                         x = torch.empty((B * npoint * ns, kp), **f32)
                         pc.group_concat_pm_wrapper(B, cin, n, npoint, ns, xyz, new_xyz, fpm, bidx, x)
