@@ -25,7 +25,6 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
-#include <cstdlib>
 
 namespace epnet {
 
@@ -1005,231 +1004,6 @@ gemm_tf32x3_ts_kernel(const GemmArgs a)
 
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Warp-specialised version of the narrow-tile kernel (round 2).  In gemm_tf32x3_ts_kernel the four producer warps are also the
-// epilogue warps and the accumulator is single-buffered, so per tile the chain "stage A into TMEM -> MMAs -> drain the accumulator"
-// runs strictly in sequence on one CTA (two CTAs per SM interleave); for the short-K layers of the backbone (K = 32 ... 128: one to
-// four k-blocks per tile) that chain, not bandwidth or the tensor pipe, set the pace (ncu r02t: 37 us for a 33 MB operand).  Here the
-// roles are separate warps of ONE CTA per SM and every hand-over is double-buffered:
-//   warps 0-3   producers: gather / copy rows with cp.async into a warp-private ring that runs ACROSS tiles (depth k-blocks ahead,
-//               whatever tile they belong to), turn them, write hi | lo into one of three TMEM operand stages;
-//   warp 4      MMA issuer (one thread), accumulators alternate between two TMEM buffers;
-//   warp 5      weight loader (one thread, bulk copies);
-//   warps 6-13  epilogue: two warps per TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ...), each taking every other
-//               32-column chunk, draining buffer b of tile i while the MMAs of tile i + 1 fill buffer b ^ 1.
-// Same arithmetic, same MMA sequence, same epilogue code as gemm_tf32x3_ts_kernel: results are bit-identical.
-// ---------------------------------------------------------------------------------------------------------------------------
-constexpr int kTs2Threads = 448;
-constexpr int kTs2Depth = 4;
-
-__global__ void __launch_bounds__(kTs2Threads, 1)
-gemm_tf32x3_ts2_kernel(const GemmArgs a)
-{
-    extern __shared__ __align__(1024) uint8_t gm_smem[];
-    __shared__ __align__(8) uint64_t full_a[kTsMaxAStages], empty_a[kTsMaxAStages], full_b[kTsMaxBStages], empty_b[kTsMaxBStages], acc_full[2],
-        acc_empty[2];
-    __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float bias_s[256 + 32];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int m_tiles = (a.L + kGmBM - 1) / kGmBM;
-    if (a.m_tiles_dev) m_tiles = min(m_tiles, __ldg(a.m_tiles_dev));
-    const int ntile = blockIdx.y;
-    const int BN = a.BN;                           // <= 64
-    const uint32_t b_bytes = (uint32_t)BN * 128;
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem) + 1023) & ~uintptr_t(1023));
-    uint8_t *b_ring = smem + (size_t)4 * kTs2Depth * 4096;
-
-    const uint32_t acc_cols = (uint32_t)((2 * BN + 31) & ~31);  // one accumulator buffer: main | correction
-    constexpr int a_stages = kTsMaxAStages;
-    const uint32_t tmem_cols = 512;                              // 2 * acc_cols (<= 256) + 3 * 64
-    const uint32_t corr_off = (uint32_t)BN;
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int my_tiles = (int)blockIdx.x < m_tiles ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < a_stages; ++s) {
-            mbar_init(&full_a[s], kGmProducers);
-            mbar_init(&empty_a[s], 1);
-        }
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(&full_b[s], 1);
-            mbar_init(&empty_b[s], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 256);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int j = tid; j < 256 + 32; j += kTs2Threads) {
-        const int n = ntile * BN + j;
-        bias_s[j] = (a.bias && j < BN && n < a.N) ? __ldg(a.bias + n) : 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_acc0 = tmem_base_slot;
-    const uint32_t tmem_a0 = tmem_acc0 + 2 * acc_cols;  // first X stage
-
-    if (warp < 4) {
-        // ===================== X producers =====================
-        const int chunk = lane & 7;   // 16-byte chunk of the 128-byte k-row
-        const int rsub = lane >> 3;   // loads: rows 32*warp + 4*i + rsub (i < 8), i.e. the warp's own TMEM lane quarter
-        uint8_t *ring = smem + (size_t)warp * kTs2Depth * 4096;
-        uint32_t st_off[8], ld_off[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + rsub;
-            st_off[i] = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-            ld_off[i] = (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4);  // chunk i of this lane's row
-        }
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        // the copy stream: k-blocks in (tile, kb) order, kTs2Depth of them in flight across tile boundaries; one cp.async group each
-        RowSource src;
-        int pf_it = 0, pf_kb = 0, pf_slot = 0;  // next block to request: tile ordinal, k-block, ring slot
-        auto request = [&]() {
-            if (pf_it < my_tiles) {
-                if (pf_kb == 0) src.init(a, ((int)blockIdx.x + pf_it * (int)gridDim.x) * kGmBM + 32 * warp + rsub, 4);
-                src.copy_async(a, pf_kb * kGmBK + chunk * 4, ring + pf_slot * 4096, st_off);
-                if (++pf_kb == a.n_kblocks) { pf_kb = 0; ++pf_it; }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");  // always a group (possibly empty): group index == block index
-            if (++pf_slot == kTs2Depth) pf_slot = 0;
-        };
-        for (int j = 0; j < kTs2Depth; ++j) request();
-        int t = 0, slot = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * kGmBM;
-            float goff[3] = {0.f, 0.f, 0.f};  // grouped operand: the sample's offset from its centre
-            if (a.g_idx && a.g_xyz) {
-                const int row = row0 + 32 * warp + lane;
-                if (row < a.L) {
-                    const float *pp = a.g_xyz + ((size_t)(row / a.g_rows_scene) * a.g_n + __ldg(a.g_idx + row)) * 3;
-                    const float *cc = a.g_centre + (size_t)(row / a.g_ns) * 3;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) goff[j] = __fsub_rn(__ldg(pp + j), __ldg(cc + j));  // as pointnet2_utils.py:252
-                }
-            }
-            for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                asm volatile("cp.async.wait_group 3;" ::: "memory");  // kTs2Depth - 1 newer groups may still be pending
-                __syncwarp();
-                uint32_t v[32];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(ring + slot * 4096 + ld_off[i]);
-                    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-                }
-                __syncwarp();  // the slot has been read by all lanes: refill it
-                request();     // goes into the slot just read (pf_slot follows slot)
-                if (a.g_idx && a.g_xyz && (kb + 1) * kGmBK > a.kcopy && kb * kGmBK < a.kcopy + 3) {  // this k-block holds offset columns
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int col = a.kcopy + j - kb * kGmBK;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (e == col) v[e] = __float_as_uint(goff[j]);
-                    }
-                }
-                mbar_wait(&empty_a[t], ph ^ 1u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_a0 + (uint32_t)t * 64u + lane_addr;
-                tmem_st32(taddr, v);  // hi: the raw words
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = __uint_as_float(v[j]);
-                    v[j] = __float_as_uint(__fsub_rn(x, __uint_as_float(v[j] & 0xffffe000u)));
-                }
-                tmem_st32(taddr + 32u, v);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(&full_a[t]);
-                if (++t == a_stages) { t = 0; ph ^= 1u; }
-                if (++slot == kTs2Depth) slot = 0;
-            }
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == 4) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 2) << 17) | ((uint32_t)(kGmBM >> 4) << 24);
-            int t = 0, s = 0;
-            uint32_t pha = 0, phb = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int buf = it & 1;
-                mbar_wait(&acc_empty[buf], (uint32_t)((it >> 1) & 1) ^ 1u);  // both epilogue warps of every quarter have drained this buffer
-                tc_fence_after();
-                const uint32_t tmem_acc = tmem_acc0 + (uint32_t)buf * acc_cols;
-                for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait(&full_a[t], pha);
-                    mbar_wait(&full_b[s], phb);
-                    tc_fence_after();
-                    const uint64_t d_bh = umma_desc_k_sw128(smem_u32(b_ring + (size_t)s * 2 * b_bytes));  // [B_hi | B_lo]: 2*BN rows
-                    const uint32_t a_hi = tmem_a0 + (uint32_t)t * 64u, a_lo = a_hi + 32u;
-#pragma unroll
-                    for (int ks = 0; ks < kGmBK / 8; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
-                        umma_tf32_ts(tmem_acc, a_hi + ks * 8, d_bh + adv, idesc2, (kb | ks) ? 1u : 0u);  // hi*hi | hi*lo
-                        umma_tf32_ts(tmem_acc + corr_off, a_lo + ks * 8, d_bh + adv, idesc, 1u);           // lo*hi
-                    }
-                    umma_commit(&empty_a[t]);
-                    umma_commit(&empty_b[s]);
-                    if (++t == a_stages) { t = 0; pha ^= 1u; }
-                    if (++s == a.stages) { s = 0; phb ^= 1u; }
-                }
-                umma_commit(&acc_full[buf]);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 5) {
-        // ===================== weight loader (one thread) =====================
-        if (lane == 0) {
-            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)ntile * a.n_kblocks * 2 * b_bytes;
-            int s = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < my_tiles; ++it)
-            for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                if (a.tile_phase && kb == 0) {  // this m-tile's weight set (sparse image tail)
-                    const int p16 = __ldg(a.tile_phase + (int)blockIdx.x + it * (int)gridDim.x);
-                    const int wt = ((p16 >> 4) % a.phase_k) * a.phase_k + ((p16 & 15) % a.phase_k);
-                    wsrc = reinterpret_cast<const uint8_t *>(a.wpack) + (size_t)wt * a.n_kblocks * 2 * b_bytes;
-                }
-                mbar_wait(&empty_b[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], 2 * b_bytes);
-                bulk_g2s(b_ring + (size_t)s * 2 * b_bytes, wsrc + (size_t)kb * 2 * b_bytes, 2 * b_bytes, &full_b[s]);
-                if (++s == a.stages) { s = 0; ph ^= 1u; }
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===================== epilogue: warps 6..13, quarter = warp % 4, every other 32-column chunk =====================
-        const int quarter = warp & 3, half = (warp - 6) >> 2;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
-            const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * kGmBM;
-            mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
-            tc_fence_after();
-            gemm_epilogue(a, tmem_acc0 + (uint32_t)buf * acc_cols, corr_off, quarter, lane, row0, ntile, bias_s, half * 32, 64);
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-        }
-    }
-
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc0), "r"(tmem_cols) : "memory");
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------------
 // FP16-split GEMM / 3x3 convolution whose A operand arrives ALREADY SPLIT (two FP16 planes written by the producing layer's
 // epilogue, GemmArgs::yh1/yh2) and is moved by TMA TENSOR loads (cp.async.bulk.tensor, SASS UTMALDG) straight into the swizzled
 // shared-memory image the MMA reads.  Compared with gemm_f16x3_kernel there are no producer warps at all: nothing is converted,
@@ -1466,18 +1240,6 @@ static int gemm_launch(GemmArgs &a, cudaStream_t st)
     if (a.BN <= 64) {  // narrow tile: X through TMEM, shared memory holds only a ring of weight k-blocks
         int stages = a.n_kblocks < kTsMaxBStages ? a.n_kblocks : kTsMaxBStages;
         a.stages = stages < 1 ? 1 : stages;
-        static const bool ts2 = [] { const char *e = getenv("EPNET_TS2"); return !(e && e[0] == '0'); }();
-        if (ts2) {  // warp-specialised, one CTA per SM, every hand-over double-buffered (gemm_tf32x3_ts2_kernel)
-            a.stages = kTsMaxBStages;  // the weight ring runs across tiles
-            a.depth = kTs2Depth;
-            const size_t smem2 = (size_t)4 * kTs2Depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
-            const int e2 = raise_limit((const void *)gemm_tf32x3_ts2_kernel);
-            if (e2) return e2;
-            const int per_ntile2 = (kSmCount + n_tiles - 1) / n_tiles;
-            if ((int)grid.x > per_ntile2) grid.x = per_ntile2;
-            gemm_tf32x3_ts2_kernel<<<grid, kTs2Threads, smem2, st>>>(a);
-            EPNET_RETURN_LAUNCH_STATUS();
-        }
         a.depth = a.n_kblocks < 3 ? a.n_kblocks : 3;  // 48 KB of X + <= 48 KB of W per CTA: two CTAs per SM
         const size_t smem = (size_t)4 * a.depth * 4096 + (size_t)a.stages * 2 * a.BN * 128 + 1024;
         const int e = raise_limit((const void *)gemm_tf32x3_ts_kernel);
