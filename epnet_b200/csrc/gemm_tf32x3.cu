@@ -315,7 +315,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
                 const int j = j4 + e;
                 float f = __fmaf_rn(__uint_as_float(w[j]), a.corr_scale, __uint_as_float(v[j])) + bb[e];  // scale 1: an exact add
                 if (a.relu) f = fmaxf(f, 0.f);
-                amax = fmaxf(amax, fabsf(f));  // padding rows/columns hold bias-only values: harmless
+                if (!(a.relu && pool > 1)) amax = fmaxf(amax, fabsf(f));  // pooled after ReLU: the guard looks at the pooled maxima instead
                 v[j] = __float_as_uint(f);
             }
         }
@@ -409,14 +409,20 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs &a, uint32_t tmem_a
                 }
             }
             // live: v[0 .. 32/pool), columns col_base + i of this lane's group
+            const int live = 32 / pool;
+            if (!mapped) amax = fmaxf(amax, __uint_as_float(v[0]));  // ReLU'd, non-negative: the pooled maxima bound every value pooled away
             if (row < a.L) {
                 float *dst = a.y + (size_t)(row / pool) * a.ldy + n0 + col_base;
-                const int live = 32 / pool;
+                if (!mapped && live == 1 && ncols == 32 && n0 + 32 <= a.N) {
+                    dst[0] = __uint_as_float(v[0]);  // the common case (nsample = 32, full chunk): one coalesced store per warp
+                } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (i < live && col_base + i < ncols && n0 + col_base + i < a.N) {
-                        const uint32_t u = v[i];
-                        dst[i] = __uint_as_float(mapped ? ((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u) : u);
+                    for (int i = 0; i < 16; ++i) {
+                        if (i < live && col_base + i < ncols && n0 + col_base + i < a.N) {
+                            const uint32_t u = v[i];
+                            dst[i] = __uint_as_float(mapped ? ((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u) : u);
+                            if (!mapped && i > 0) amax = fmaxf(amax, __uint_as_float(u));
+                        }
                     }
                 }
             }
