@@ -129,6 +129,14 @@ def sweep_rooflines(device, peak):
     xy = (torch.rand(1, n, 2, generator=g) * 2 - 1).to(device)
     out = torch.empty(1, C, n, device=device)
     add("grid_gather_bilinear", (1, C, H, W, n), lambda: pc.grid_gather_bilinear_wrapper(1, C, H, W, n, fmap, xy, False, out))
+    # the same gather from an NHWC map (the layout of the runner's image stream): every tap is one contiguous, 128-bit vectorised channel run
+    fmap_nhwc = fmap.permute(0, 2, 3, 1).contiguous()
+    out_pm = torch.empty(n, C, device=device)
+    t = _event_time(lambda: pc.grid_gather_nhwc_pm_wrapper(1, C, H, W, n, fmap_nhwc, xy, False, out_pm))
+    by = algorithmic_bytes("grid_gather_nhwc_pm", (1, C, H, W, n))
+    rows.append({"op": "grid_gather_nhwc_pm", "shape": [1, C, H, W, n], "us": round(t * 1e6, 1), "algorithmic_mb": round(by / 1e6, 1),
+                 "achieved_gbs": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak, 3)})
+    del fmap, fmap_nhwc, out_pm
     # point-major fused kernels (the runner's path): a gathered point is one contiguous row
     C, N, M, ns = 128, 65536, 16384, 32
     xyz = torch.randn(1, N, 3, device=device)

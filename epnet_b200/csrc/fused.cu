@@ -279,7 +279,19 @@ group_concat_pm_kernel(int c, int n, int m, int ns, const float *__restrict__ xy
     const float *pbase = xyz + (size_t)scene * n * 3;
     const float *crow = new_xyz + (size_t)centre * 3;
     float *orow = out + (size_t)row0 * ldo;
-    for (int ch = chunk0; ch < chunks; ch += step) {
+    int chunks_here = chunks;
+    if (vec_ok && (c & 3) == 0 && step >= 4) {
+        // the last chunk holds only the three re-centred coordinates: lanes 0..3 of the group write it for rows 0..3 of the quad in the same
+        // pass, instead of one lane walking it in a second pass of the whole group (33 chunks over 32 lanes at C = 128)
+        chunks_here = c >> 2;
+        if (chunk0 < 4) {
+            const float *p = pbase + (size_t)srcs[chunk0] * 3;
+            const float4 t = make_float4(__fsub_rn(__ldg(p), __ldg(crow)), __fsub_rn(__ldg(p + 1), __ldg(crow + 1)),
+                                         __fsub_rn(__ldg(p + 2), __ldg(crow + 2)), 0.f);
+            __stcs(reinterpret_cast<float4 *>(orow + (size_t)chunk0 * ldo + c), t);
+        }
+    }
+    for (int ch = chunk0; ch < chunks_here; ch += step) {
         const int k0 = ch * 4;
         float4 v[4];
         if (vec_ok && k0 + 4 <= c) {
