@@ -21,6 +21,13 @@ constexpr int kSmCount = 148;  // B200
 constexpr int kStagedNotApplicable = -2;
 int launch_staged_rows(bool interp, int b, int c, int len, long long e_total, const float *src, const int *idx, const float *weight,
                        float *out, cudaStream_t st);
+// does a (len)-float row fit the staged kernels' shared memory whole?
+bool staged_row_fits(int len);
+// transposed_rows.cu: the same channel-major ops through a point-major scratch copy (any row length); kStagedNotApplicable likewise
+int launch_transposed_gather(bool interp, bool staged_fits, int b, int c, int len, long long e_total, const float *src, const int *idx,
+                             const float *weight, float *out, cudaStream_t st);
+int launch_transposed_scatter(bool interp, int b, int c, int len, long long e_total, const float *grad_out, const int *idx,
+                              const float *weight, float *grad_points, cudaStream_t st);
 
 // Squared distance with the exact rounding sequence of the reference kernels as compiled by nvcc -O2
 // (PTX: sub,sub,mul,fma,sub,fma): d = fma(dz,dz, fma(dx,dx, dy*dy)), each difference taken as (a - b).

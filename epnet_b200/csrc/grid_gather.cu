@@ -4,8 +4,12 @@
 //
 // ATen's generic grid_sampler_2d recomputes the four tap addresses and weights for every (point,
 // channel) pair.  Here a thread owns one point: tap offsets/weights are computed once and reused for
-// kGgChannels channel planes; the per-channel work is 4 L2 gathers, 4 FMAs and one store that is
-// coalesced across the warp (consecutive threads = consecutive points of the (B,C,N) output).
+// kGgChannels channel planes; the per-channel work is 4 FMAs and one store that is coalesced across the
+// warp (consecutive threads = consecutive points of the (B,C,N) output).  The taps of different points lie
+// in different 32-byte sectors, so the kernel is bound by the SM's sector-request rate, not by bytes: the
+// two taps of an image row are therefore fetched with ONE aligned 128-bit load (the 4-pixel group holding
+// x0; only when x0 is the last pixel of its group, one lane in four, does x1 need a second, scalar load) --
+// 2.5 requests per output instead of 4.  Needs W % 4 == 0 and a 16-byte aligned map; otherwise four scalar loads.
 // Arithmetic follows ATen (unnormalise, floor, weights as products of corner distances, taps added in
 // the order nw, ne, sw, se); results agree with grid_sample to ~1e-7, the test tolerance is 1e-5.
 #include "common.cuh"
@@ -48,6 +52,23 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int h, int w, int 
     return t;
 }
 
+// the two horizontally adjacent taps (x0, x0+1) of row `row` (a pointer to the start of that image row): out-of-image taps read as 0
+__device__ __forceinline__ void row_pair(const float *__restrict__ row, int x0, int w, bool y_in, float &west, float &east)
+{
+    west = east = 0.f;
+    if (!y_in) return;
+    if (x0 >= 0 && x0 < w) {
+        const int q = x0 & 3;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(row + (x0 - q)));
+        west = q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
+        if (q < 3) east = q == 0 ? v.y : q == 1 ? v.z : v.w;
+        else if (x0 + 1 < w) east = __ldg(row + x0 + 1);
+    } else if (x0 == -1) {
+        east = __ldg(row);
+    }
+}
+
+template <bool kVec>
 __global__ void __launch_bounds__(kGgThreads)
 grid_gather_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, const float *__restrict__ xy, int align_corners,
                    float *__restrict__ out)
@@ -62,6 +83,33 @@ grid_gather_kernel(int c, int h, int w, int n, const float *__restrict__ fmap, c
     const Taps t = make_taps(g.x, g.y, h, w, align_corners);
     const int c_begin = blockIdx.y * kGgChannels;
     const int c_end = min(c, c_begin + kGgChannels);
+    if (kVec) {
+        float ix, iy;  // the same unnormalisation as make_taps, for the integer corner
+        if (align_corners) {
+            ix = __fmul_rn(__fmul_rn(__fadd_rn(g.x, 1.f), 0.5f), (float)(w - 1));
+            iy = __fmul_rn(__fmul_rn(__fadd_rn(g.y, 1.f), 0.5f), (float)(h - 1));
+        } else {
+            ix = __fmul_rn(__fmaf_rn(__fadd_rn(g.x, 1.f), (float)w, -1.f), 0.5f);
+            iy = __fmul_rn(__fmaf_rn(__fadd_rn(g.y, 1.f), (float)h, -1.f), 0.5f);
+        }
+        // a point far outside the image has no tap: clamp before the int conversion so that x0 + 1 cannot overflow
+        const int x0 = (int)fminf(fmaxf(floorf(ix), -2.f), (float)w), y0 = (int)fminf(fmaxf(floorf(iy), -2.f), (float)h);
+        const bool yin0 = y0 >= 0 && y0 < h, yin1 = y0 + 1 >= 0 && y0 + 1 < h;
+        const size_t r0 = (size_t)(yin0 ? y0 : 0) * w, r1 = (size_t)(yin1 ? y0 + 1 : 0) * w;
+#pragma unroll 4
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            const float *p = fmap + (size_t)ch * plane;
+            float nw, ne, sw, se;
+            row_pair(p + r0, x0, w, yin0, nw, ne);
+            row_pair(p + r1, x0, w, yin1, sw, se);
+            float acc = __fmul_rn(nw, t.w[0]);
+            acc = __fmaf_rn(ne, t.w[1], acc);
+            acc = __fmaf_rn(sw, t.w[2], acc);
+            acc = __fmaf_rn(se, t.w[3], acc);
+            out[(size_t)ch * n + i] = acc;
+        }
+        return;
+    }
 #pragma unroll 4
     for (int ch = c_begin; ch < c_end; ++ch) {
         const float *p = fmap + (size_t)ch * plane;
@@ -106,7 +154,10 @@ EPNET_API int epnet_grid_gather_bilinear(int b, int c, int h, int w, int n, cons
     if ((reinterpret_cast<uintptr_t>(xy) & 7) != 0) return EPNET_ERR_BAD_ARG;
     if (b == 0 || c == 0 || n == 0) return EPNET_OK;
     dim3 grid((n + kGgThreads - 1) / kGgThreads, (c + kGgChannels - 1) / kGgChannels, b);
-    grid_gather_kernel<<<grid, kGgThreads, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out);
+    if (w % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15) == 0)
+        grid_gather_kernel<true><<<grid, kGgThreads, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out);
+    else
+        grid_gather_kernel<false><<<grid, kGgThreads, 0, (cudaStream_t)stream>>>(c, h, w, n, fmap, xy, align_corners, out);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 

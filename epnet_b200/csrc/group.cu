@@ -103,6 +103,8 @@ row_scatter_add_kernel(int c, int n, long long e_total, const float *__restrict_
 static int launch_gather(int b, int c, int n, long long e_total, const float *points, const int *idx, float *out, cudaStream_t st)
 {
     if (b == 0 || c == 0 || e_total == 0) return EPNET_OK;
+    const int turned = launch_transposed_gather(false, staged_row_fits(n), b, c, n, e_total, points, idx, nullptr, out, st);
+    if (turned != kStagedNotApplicable) return turned;
     const int staged = launch_staged_rows(false, b, c, n, e_total, points, idx, nullptr, out, st);
     if (staged != kStagedNotApplicable) return staged;
     const uintptr_t al = reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out);
@@ -116,6 +118,8 @@ static int launch_scatter(int b, int c, int n, long long e_total, const float *g
                           cudaStream_t st)
 {
     if (b == 0 || c == 0 || e_total == 0) return EPNET_OK;
+    const int turned = launch_transposed_scatter(false, b, c, n, e_total, grad_out, idx, nullptr, grad_points, st);
+    if (turned != kStagedNotApplicable) return turned;
     const uintptr_t al = reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(grad_out);
     const int vec_ok = (e_total % 4 == 0) && ((al & 15) == 0);
     dim3 grid((unsigned)(((e_total + 3) / 4 + kGatherThreads - 1) / kGatherThreads), (c + kRowsPerThread - 1) / kRowsPerThread, b);

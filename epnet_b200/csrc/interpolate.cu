@@ -278,6 +278,8 @@ EPNET_API int epnet_three_interpolate(int b, int c, int m, int n, const float *p
     using namespace epnet;
     if (b < 0 || c < 0 || m < 0 || n < 0 || !points || !idx || !weight || !out) return EPNET_ERR_BAD_ARG;
     if (b == 0 || c == 0 || n == 0) return EPNET_OK;
+    const int turned = launch_transposed_gather(true, staged_row_fits(m), b, c, m, n, points, idx, weight, out, (cudaStream_t)stream);
+    if (turned != kStagedNotApplicable) return turned;
     const int staged = launch_staged_rows(true, b, c, m, n, points, idx, weight, out, (cudaStream_t)stream);
     if (staged != kStagedNotApplicable) return staged;
     dim3 grid(((n + 3) / 4 + kIpThreads - 1) / kIpThreads, (c + kIpChannels - 1) / kIpChannels, b);
@@ -293,6 +295,8 @@ EPNET_API int epnet_three_interpolate_grad(int b, int c, int n, int m, const flo
     using namespace epnet;
     if (b < 0 || c < 0 || m < 0 || n < 0 || !grad_out || !idx || !weight || !grad_points) return EPNET_ERR_BAD_ARG;
     if (b == 0 || c == 0 || n == 0) return EPNET_OK;
+    const int turned = launch_transposed_scatter(true, b, c, m, n, grad_out, idx, weight, grad_points, (cudaStream_t)stream);
+    if (turned != kStagedNotApplicable) return turned;
     dim3 grid((n + kIpThreads - 1) / kIpThreads, (c + kIpChannels - 1) / kIpChannels, b);
     three_interpolate_grad_kernel<<<grid, kIpThreads, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight, grad_points);
     EPNET_RETURN_LAUNCH_STATUS();

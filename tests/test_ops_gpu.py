@@ -103,7 +103,9 @@ def test_three_nn_bit_exact(ours, kind, n, m):
 
 @pytest.mark.parametrize("c,m,n", [(8, 64, 256), (3, 10, 17), (256, 4096, 16384), (33, 100, 1001),
                                    # rows staged in shared memory: ragged last row group; one 128 KB row per CTA; partly staged 240 KB row
-                                   (70, 1024, 16384), (9, 32768, 131072), (5, 60000, 240000)])
+                                   (70, 1024, 16384), (9, 32768, 131072), (5, 60000, 240000),
+                                   # through the point-major scratch copy: ragged channel quad and ragged last tile
+                                   (45, 50000, 100003)])
 def test_three_interpolate(ours, c, m, n):
     rng = np.random.RandomState(41)
     pts = rng.randn(2, c, m).astype(np.float32)
@@ -121,8 +123,12 @@ def test_three_interpolate(ours, c, m, n):
 
 # ------------------------------------------------------------------ gather / group
 @pytest.mark.parametrize("c,n,m,ns", [(3, 100, 30, 16), (96, 4096, 1024, 32), (5, 77, 13, 3), (64, 16384, 4096, 16),
-                                      # staged rows: ragged row group; 160 KB rows; partly staged 256 KB rows; staged gather_points; rows too long to stage
-                                      (40, 4096, 1024, 32), (20, 40000, 4096, 32), (7, 65536, 2048, 64), (300, 1024, 4096, 16), (5, 250000, 4096, 64)])
+                                      # staged rows: ragged row group; 160 KB rows; 256 KB rows below / above the work threshold (two parts); staged
+                                      # gather_points; 1 MB rows in five parts; gather_points with fewer outputs than row elements; rows too long to stage
+                                      (40, 4096, 1024, 32), (20, 40000, 4096, 32), (7, 65536, 2048, 64), (9, 65536, 2048, 64), (300, 1024, 4096, 16),
+                                      (5, 250000, 4096, 64), (300, 16384, 4096, 16), (3, 600000, 8192, 64),
+                                      # rows longer than shared memory with enough work: through the point-major scratch copy (one / two channel chunks)
+                                      (20, 65536, 4096, 32), (133, 60000, 2048, 32)])
 def test_group_and_gather(ours, c, n, m, ns):
     rng = np.random.RandomState(51)
     pts = rng.randn(2, c, n).astype(np.float32)
