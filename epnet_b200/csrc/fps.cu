@@ -92,7 +92,7 @@ template <int NW, int kBuckets, int kSlots, bool kCluster>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
                   float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim, int csize,
-                  int slice)
+                  int slice, const int *__restrict__ skip)
 {
     constexpr int T = NW * 32;
     constexpr int CAP = T * kBuckets * kSlots;  // sorted positions this CTA can hold
@@ -122,6 +122,7 @@ fps_bucket_kernel(int n_total, int m, int L, int qbits, const float *__restrict_
     __shared__ __align__(16) FpsClusterCand cslots[2][8];
 
     const int scene = kCluster ? blockIdx.x / csize : blockIdx.x;
+    if (skip && __ldg(skip + scene)) return;  // answered by fps_prefix_fill_kernel (every CTA of a cluster takes the same branch)
     const int rank = kCluster ? blockIdx.x % csize : 0;   // == %cluster_ctarank for a 1-D cluster
     const int first = rank * slice;                        // first original index owned by this CTA
     const int n = kCluster ? min(slice, n_total - first) : n_total;  // points owned by this CTA
@@ -467,10 +468,12 @@ __device__ __forceinline__ uint32_t fps_tie_decode(uint32_t tie, int L)
 
 __global__ void __launch_bounds__(1024, 1)
 fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
-                     float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
+                     float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim,
+                     const int *__restrict__ skip)
 {
     __shared__ FpsCand slots[2][32];
     const int scene = blockIdx.x;
+    if (skip && __ldg(skip + scene)) return;
     xyz += (size_t)scene * n * 3;
     temp += (size_t)scene * n;
     idx += (size_t)scene * m;
@@ -523,12 +526,14 @@ fps_streaming_kernel(int n, int m, const float *__restrict__ xyz, float *__restr
 template <int PPL>
 __global__ void __launch_bounds__(128)
 fps_warp_kernel(int scenes, int n, int m, int L, int qbits, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx,
-                float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim)
+                float *__restrict__ new_xyz, const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim,
+                const int *__restrict__ skip)
 {
     __shared__ float s_xyz[4][PPL * 32 * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scene = blockIdx.x * 4 + warp;
     if (scene >= scenes) return;
+    if (skip && __ldg(skip + scene)) return;  // no block barrier in this kernel: a warp may leave on its own
     xyz += (size_t)scene * n * 3;
     temp += (size_t)scene * n;
     idx += (size_t)scene * m;
@@ -582,27 +587,27 @@ fps_warp_kernel(int scenes, int n, int m, int L, int qbits, const float *__restr
 
 template <int PPL>
 static int launch_warp(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
-                       const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
+                       const float *aux_in, float *aux_out, int aux_dim, const int *skip, cudaStream_t st)
 {
-    fps_warp_kernel<PPL><<<(b + 3) / 4, 128, 0, st>>>(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
+    fps_warp_kernel<PPL><<<(b + 3) / 4, 128, 0, st>>>(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, skip);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
 template <int NW, int kBuckets, int kSlots>
 static int launch_bucket(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
-                         const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st)
+                         const float *aux_in, float *aux_out, int aux_dim, const int *skip, cudaStream_t st)
 {
     const size_t smem = (size_t)3 * NW * 32 * kBuckets * kSlots * sizeof(float);
     auto kernel = fps_bucket_kernel<NW, kBuckets, kSlots, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kernel<<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, 1, n);
+    kernel<<<b, NW * 32, smem, st>>>(n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, 1, n, skip);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
 // 16384 < N <= 8 * 16384: a thread-block cluster of ceil(N / 16384) CTAs per scene, each with the full resident layout
 static int launch_cluster(int b, int n, int m, int L, int qbits, const float *xyz, float *temp, int *idx, float *new_xyz,
-                          const float *aux_in, float *aux_out, int aux_dim, cudaStream_t st, int force_csize = 0)
+                          const float *aux_in, float *aux_out, int aux_dim, const int *skip, cudaStream_t st, int force_csize = 0)
 {
     constexpr int NW = 16, KB = 8, KS = 4;
     const int csize = force_csize > 0 ? force_csize : (n + kFpsMaxResident - 1) / kFpsMaxResident;
@@ -623,7 +628,7 @@ static int launch_cluster(int b, int n, int m, int L, int qbits, const float *xy
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kernel, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, csize, slice);
+    e = cudaLaunchKernelEx(&cfg, kernel, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, csize, slice, skip);
     if (e != cudaSuccess) return (int)e;
     EPNET_RETURN_LAUNCH_STATUS();
 }
@@ -631,7 +636,7 @@ static int launch_cluster(int b, int n, int m, int L, int qbits, const float *xy
 }  // namespace epnet
 
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
-                        float *aux_out, int aux_dim, void *stream)
+                        float *aux_out, int aux_dim, const int *skip, void *stream)
 {
     using namespace epnet;
     if (b < 0 || n <= 0 || m < 0 || !xyz || !temp || !idx) return EPNET_ERR_BAD_ARG;
@@ -644,7 +649,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         const int q = (n + (1 << L) - 1) >> L;  // points per reference thread
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
-#define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st
+#define EPNET_FPS_ARGS b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, skip, st
         if (n <= 128) return launch_warp<4>(EPNET_FPS_ARGS);            // one warp per scene, points in registers, no buckets
         if (n <= 256) return launch_warp<8>(EPNET_FPS_ARGS);
         if (n <= 512) return launch_warp<16>(EPNET_FPS_ARGS);
@@ -653,7 +658,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         {   // experiment switch: spread one scene of <= 16384 points over a cluster of 2 / 4 CTAs (DSMEM exchange per iteration)
             static const int forced = [] { const char *e = getenv("EPNET_FPS_CLUSTER"); return e ? atoi(e) : 0; }();
             if (forced > 1 && forced <= 8 && n >= 8192)
-                return launch_cluster(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st, forced);
+                return launch_cluster(b, n, m, L, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, skip, st, forced);
         }
         return launch_bucket<16, 8, 4>(EPNET_FPS_ARGS);                 // 128 buckets of 128
         // (measured alternatives: 8 warps x 16 buckets is 27 % slower at N = 16384 -- touched buckets of one warp update
@@ -664,19 +669,128 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         const int q = (n + 1023) >> 10;
         int qbits = 0;
         while ((1 << qbits) < q) ++qbits;
-        return launch_cluster(b, n, m, 10, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, st);
+        return launch_cluster(b, n, m, 10, qbits, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, skip, st);
     }
-    fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim);
+    fps_streaming_kernel<<<b, 1024, 0, st>>>(n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, skip);
     EPNET_RETURN_LAUNCH_STATUS();
 }
 
 EPNET_API int epnet_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream)
 {
-    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, nullptr, nullptr, 0, stream);
+    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, nullptr, nullptr, 0, nullptr, stream);
 }
 
 EPNET_API int epnet_fps_sample(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
                                float *aux_out, int aux_dim, void *stream)
 {
-    return fps_dispatch(b, n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, stream);
+    return fps_dispatch(b, n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, nullptr, stream);
+}
+
+// ---- sampling a cloud that is already in furthest-point order ------------------------------------------------------------------------
+// The set-abstraction levels sample 16384 -> 4096 -> 1024 -> 256 -> 64: every level after the first samples the previous level's OUTPUT,
+// which is in furthest-point order, so its answer is the identity 0..m-1 -- the arg-max of step s over the sub-cloud is the point the
+// first level took at step s over the whole cloud -- unless two points of the sub-cloud tie for a maximum (then the tie rules of the two
+// levels, which depend on array positions, may differ).  epnet_fps_prefix_check decides that exactly, in O(n*m) parallel work instead
+// of m dependent arg-max steps: with T_j(s) = min(1e10, d(p_j,p_0), ..., d(p_j,p_{s-1})) (the running distances furthest-point sampling
+// holds at step s if it has returned 0..s-1 so far, evaluated with the same fma chain) it sets flag = 1 iff T_j(s) < T_s(s) for every
+// step 1 <= s < m and every j != s: the arg-max of every step is unique and is s, so the identity is what the sampling kernel returns,
+// whatever its tie rule.  Because the condition for (n', m') with n' <= n, m' <= m is a subset of the one for (n, m), one check of the
+// second level also covers the later ones.  epnet_fps_sample_guarded then answers flagged scenes with the prefix and runs the real
+// sampling for the others (lattices, duplicated points, anything not in furthest-point order): bit-exact either way.
+namespace epnet {
+
+constexpr int kPrefixThreads = 128;
+constexpr int kPrefixMaxM = 2048;  // the first m points and their winning distances sit in shared memory
+
+__global__ void __launch_bounds__(kPrefixThreads)
+fps_prefix_winners_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ winners, int *__restrict__ flag)
+{
+    __shared__ float4 pts[kPrefixMaxM];
+    const int scene = blockIdx.y;
+    xyz += (size_t)scene * n * 3;
+    const int s = blockIdx.x * kPrefixThreads + threadIdx.x;
+    const int need = min(m, (blockIdx.x + 1) * kPrefixThreads);  // this CTA's steps look at points below their own index
+    for (int i = threadIdx.x; i < need; i += kPrefixThreads)
+        pts[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), 0.f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) flag[scene] = 1;  // fps_prefix_check_kernel (next in the stream) clears it
+    __syncthreads();
+    if (s >= m) return;
+    const float4 p = pts[s];
+    float t = 1e10f;
+#pragma unroll 8
+    for (int i = 0; i < s; ++i) {
+        const float4 q = pts[i];
+        t = fminf(sqdist_ref(p.x, p.y, p.z, q.x, q.y, q.z), t);
+    }
+    winners[(size_t)scene * m + s] = t;
+}
+
+__global__ void __launch_bounds__(kPrefixThreads)
+fps_prefix_check_kernel(int n, int m, const float *__restrict__ xyz, const float *__restrict__ winners, int *__restrict__ flag)
+{
+    __shared__ float4 pts[kPrefixMaxM];  // .w = the winning distance of the step that picks this point
+    const int scene = blockIdx.y;
+    xyz += (size_t)scene * n * 3;
+    winners += (size_t)scene * m;
+    for (int i = threadIdx.x; i < m; i += kPrefixThreads)
+        pts[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), __ldg(winners + i));
+    __syncthreads();
+    const int j = blockIdx.x * kPrefixThreads + threadIdx.x;
+    if (j >= n) return;
+    const float px = __ldg(xyz + 3 * j), py = __ldg(xyz + 3 * j + 1), pz = __ldg(xyz + 3 * j + 2);
+    float t = 1e10f;
+    bool ok = true;
+    float4 prev = pts[0];
+#pragma unroll 8
+    for (int s = 1; s < m; ++s) {
+        const float4 cur = pts[s];
+        t = fminf(sqdist_ref(px, py, pz, prev.x, prev.y, prev.z), t);  // T_j(s)
+        ok = ok && (j == s || t < cur.w);                               // NaN fails the comparison: no shortcut
+        prev = cur;
+    }
+    if (!ok) flag[scene] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+fps_prefix_fill_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ idx, float *__restrict__ new_xyz,
+                       const float *__restrict__ aux_in, float *__restrict__ aux_out, int aux_dim, const int *__restrict__ flag)
+{
+    const int scene = blockIdx.y;
+    if (!__ldg(flag + scene)) return;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= m) return;
+    idx[(size_t)scene * m + k] = k;
+    if (new_xyz)
+        for (int a = 0; a < 3; ++a) new_xyz[((size_t)scene * m + k) * 3 + a] = __ldg(xyz + ((size_t)scene * n + k) * 3 + a);
+    if (aux_out)
+        for (int a = 0; a < aux_dim; ++a) aux_out[((size_t)scene * m + k) * aux_dim + a] = __ldg(aux_in + ((size_t)scene * n + k) * aux_dim + a);
+}
+
+}  // namespace epnet
+
+EPNET_API int epnet_fps_prefix_check(int b, int n, int m, const float *xyz, float *winners, int *flag, void *stream)
+{
+    using namespace epnet;
+    if (b < 0 || n <= 0 || m <= 0 || m > n || !xyz || !winners || !flag) return EPNET_ERR_BAD_ARG;
+    if (b == 0) return EPNET_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m > kPrefixMaxM || b > 65535) {  // no shortcut: every scene runs the real sampling
+        cudaError_t e = cudaMemsetAsync(flag, 0, (size_t)b * sizeof(int), st);
+        return e == cudaSuccess ? EPNET_OK : (int)e;
+    }
+    fps_prefix_winners_kernel<<<dim3((m + kPrefixThreads - 1) / kPrefixThreads, b), kPrefixThreads, 0, st>>>(n, m, xyz, winners, flag);
+    fps_prefix_check_kernel<<<dim3((n + kPrefixThreads - 1) / kPrefixThreads, b), kPrefixThreads, 0, st>>>(n, m, xyz, winners, flag);
+    EPNET_RETURN_LAUNCH_STATUS();
+}
+
+EPNET_API int epnet_fps_sample_guarded(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
+                                       float *aux_out, int aux_dim, const int *identity, void *stream)
+{
+    using namespace epnet;
+    if (!identity || m > n) return EPNET_ERR_BAD_ARG;
+    const int rc = fps_dispatch(b, n, m, xyz, temp, idx, new_xyz, aux_in, aux_out, aux_dim, identity, stream);
+    if (rc != EPNET_OK || b == 0 || m == 0) return rc;
+    if (b > 65535) return EPNET_ERR_BAD_ARG;
+    fps_prefix_fill_kernel<<<dim3((m + 255) / 256, b), 256, 0, (cudaStream_t)stream>>>(n, m, xyz, idx, new_xyz, aux_in, aux_out, aux_dim, identity);
+    EPNET_RETURN_LAUNCH_STATUS();
 }

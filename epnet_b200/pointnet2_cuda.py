@@ -166,6 +166,20 @@ def fps_sample_wrapper(b, n, m, xyz, temp, idx, new_xyz=None, aux_in=None, aux_o
           _opt(aux_out, torch.float32, "aux_out"), aux_dim)
 
 
+def fps_prefix_check_wrapper(b, n, m, xyz, winners, flag):
+    """flag[s] = 1 iff furthest-point sampling of m of the n points of xyz[s] (temp = 1e10) is exactly the identity 0..m-1, every
+    arg-max unique (csrc/fps.cu); winners (B, m) float32 scratch, flag (B,) int32"""
+    _call("fps_prefix_check", LIB.epnet_fps_prefix_check, xyz, b, n, m, _f(xyz, "xyz"), _f(winners, "winners"), _i(flag, "flag"))
+
+
+def fps_sample_guarded_wrapper(b, n, m, xyz, temp, idx, identity, new_xyz=None, aux_in=None, aux_out=None):
+    """fps_sample_wrapper, except that scenes with identity[s] != 0 (fps_prefix_check_wrapper) are answered with the prefix"""
+    aux_dim = 0 if aux_in is None else aux_in.shape[-1]
+    _call("fps_sample_guarded", LIB.epnet_fps_sample_guarded, xyz, b, n, m, _f(xyz, "xyz"), _f(temp, "temp"), _i(idx, "idx"),
+          _opt(new_xyz, torch.float32, "new_xyz"), _opt(aux_in, torch.float32, "aux_in"),
+          _opt(aux_out, torch.float32, "aux_out"), aux_dim, _i(identity, "identity"))
+
+
 def group_concat_wrapper(b, c, n, m, nsample, xyz, new_xyz, features, idx, out):
     _call("group_concat", LIB.epnet_group_concat, xyz, b, c, n, m, nsample, _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
           _opt(features, torch.float32, "features"), _i(idx, "idx"), _f(out, "out"))

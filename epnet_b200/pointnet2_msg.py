@@ -175,7 +175,8 @@ class Pointnet2MSG(nn.Module):
             pre_channel = c.fp_mlps[k + 1][-1] if k + 1 < len(c.fp_mlps) else channel_out
             self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k])))
 
-    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, pipeline=1, f16=True, sparse_tail=True):
+    def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, pipeline=1, f16=True, sparse_tail=True,
+                    prefix_fps=True):
         """Inference fast path (eval mode): one CUDA graph with the FPS chain, the image stream and the point
         stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py.
         f16=False keeps every GEMM on the TF32 operand split (fp32 range; see BackboneRunner); sparse_tail=False evaluates the final
@@ -183,8 +184,9 @@ class Pointnet2MSG(nn.Module):
         from .runner import BackboneRunner, PipelinedRunner
         if pipeline > 1:
             return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, f16=f16,
-                                   sparse_tail=sparse_tail)
-        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, f16=f16, sparse_tail=sparse_tail)
+                                   sparse_tail=sparse_tail, prefix_fps=prefix_fps)
+        return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, f16=f16, sparse_tail=sparse_tail,
+                              prefix_fps=prefix_fps)
 
     @staticmethod
     def _break_up_pc(pc):

@@ -92,7 +92,8 @@ class _FusionPM:
         return self.fuse(cat, relu=True, out=out, out_cm=out_cm)
 
 class BackboneRunner:
-    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True, sparse_tail=True):
+    def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True, sparse_tail=True,
+                 prefix_fps=True):
         """Point-major activations + tcgen05 fp32-grade GEMMs.
         f16: the wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE), which needs activations and folded weights
         below 65504 in magnitude (they are below 10 for the published configuration).  Guarded twice: a layer whose folded
@@ -105,6 +106,10 @@ class BackboneRunner:
         # sparse_tail: evaluate the final image fusion (transposed convolutions + 1x1 conv, pointnet2_msg.py:237-243) only at the
         # <= 4 taps of every point (sparse_tail.py) instead of over the whole up-sampled canvas; False keeps the dense form
         self.want_sparse_tail = bool(sparse_tail)
+        # prefix_fps: levels 2.. sample the previous level's output, which is in furthest-point order: one parallel check after level 1
+        # (csrc/fps.cu: epnet_fps_prefix_check) proves that their answer is the identity prefix -- or, on a tie, lets the sampling
+        # kernels run; bit-exact either way.  False always runs the sampling kernels.
+        self.prefix_fps = bool(prefix_fps)
         self.image_hw = tuple(image_hw)
         self.overflow = OverflowFlag(device)
         self._last_stream = None
@@ -148,6 +153,7 @@ class BackboneRunner:
         self.s_scale = [torch.cuda.Stream(device=device)]  # second grouping scale of a set-abstraction level
         self.s_geo = [torch.cuda.Stream(device=device) for _ in range(3)]  # geometry-only work: ball queries (2 scales), three_nn
         self.kernel_launches_per_replay = 0
+        self.fps_identity = None  # (B,) int32 after a call: 1 where levels 2.. were answered by the prefix
         self.graph = None
         self.out = None
         if use_graph:
@@ -173,13 +179,24 @@ class BackboneRunner:
         with torch.cuda.stream(self.s_fps), _nvtx("fps_chain"):
             self.s_fps.wait_event(ready)
             cur_xyz, cur_xy = xyz0, xyn
-            for npoint, _ in self.sa:
+            npoints = [npoint for npoint, _ in self.sa]
+            nested = all(a >= b for a, b in zip([N] + npoints, npoints))
+            identity = None
+            for li, (npoint, _) in enumerate(self.sa):
                 n = cur_xyz.shape[1]
                 temp = torch.full((B, n), 1e10, **f32)
                 idx = torch.empty((B, npoint), dtype=torch.int32, device=dev)
                 new_xyz = torch.empty((B, npoint, 3), **f32)
                 new_xy = torch.empty((B, npoint, 2), **f32) if c.li_fusion else None
-                pc.fps_sample_wrapper(B, n, npoint, cur_xyz, temp, idx, new_xyz, cur_xy, new_xy)
+                if identity is None:
+                    pc.fps_sample_wrapper(B, n, npoint, cur_xyz, temp, idx, new_xyz, cur_xy, new_xy)
+                else:
+                    pc.fps_sample_guarded_wrapper(B, n, npoint, cur_xyz, temp, idx, identity, new_xyz, cur_xy, new_xy)
+                if li == 0 and self.prefix_fps and nested and len(npoints) > 1 and npoints[1] <= 2048:
+                    # the check of level 2 (n = npoints[0], m = npoints[1]) contains the conditions of every later level
+                    identity = torch.empty((B,), dtype=torch.int32, device=dev)
+                    pc.fps_prefix_check_wrapper(B, npoint, npoints[1], new_xyz, torch.empty((B, npoints[1]), **f32), identity)
+                    self.fps_identity = identity
                 ev = torch.cuda.Event()
                 ev.record(self.s_fps)
                 fps_done.append(ev)

@@ -92,6 +92,18 @@ int epnet_grid_gather_bilinear_grad(int b, int c, int h, int w, int n, const flo
 int epnet_fps_sample(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
                      float *aux_out, int aux_dim, void *stream);
 
+/* The levels of the backbone sample each other's output (pointnet2_msg.py:141-153 stacks PointnetSAModuleMSG with npoint 4096, 1024,
+ * 256, 64; each calls furthest_point_sample on the previous level's new_xyz, pointnet2_modules.py:38-42), and a cloud that is already
+ * in furthest-point order samples to the identity unless two of its points tie for a maximum.
+ *   epnet_fps_prefix_check: flag[s] = 1 iff sampling m of the n points of xyz[s] from temp = 1e10 returns exactly 0..m-1 with every
+ *     arg-max unique (decided in O(n*m) parallel work); one check for (n, m) also holds for every (n' <= n, m' <= m) prefix.
+ *     winners (B,m) scratch; flag (B) int; m <= 2048, larger m clears the flags.
+ *   epnet_fps_sample_guarded: epnet_fps_sample, except that scenes with identity[s] != 0 get idx = 0..m-1, new_xyz / aux_out = the
+ *     first m rows of xyz / aux_in (their temp is left untouched); the others run the real sampling.  Bit-exact either way. */
+int epnet_fps_prefix_check(int b, int n, int m, const float *xyz, float *winners, int *flag, void *stream);
+int epnet_fps_sample_guarded(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
+                             float *aux_out, int aux_dim, const int *identity, void *stream);
+
 /* QueryAndGroup.forward minus the ball query (pointnet2_utils.py:250-257) in one launch:
  *   out (B,3+C,M,ns): rows 0..2 = xyz[idx] - new_xyz (re-centred coordinates), rows 3.. = features[:, idx].
  * xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL with c = 0, idx (B,M,ns). */
