@@ -26,6 +26,7 @@ SIGNATURES = {
     "epnet_grid_gather_bilinear_grad": [_c_int] * 5 + [_c_void_p] * 2 + [_c_int] + [_c_void_p] * 2,
     "epnet_fps_sample": [_c_int] * 3 + [_c_void_p] * 6 + [_c_int, _c_void_p],
     "epnet_fps_prefix_check": [_c_int] * 3 + [_c_void_p] * 4,
+    "epnet_sa_first_level": [_c_int] * 7 + [_c_void_p] * 5 + [_c_int, _c_void_p],
     "epnet_fps_sample_guarded": [_c_int] * 3 + [_c_void_p] * 6 + [_c_int, _c_void_p, _c_void_p],
     "epnet_group_concat": [_c_int] * 5 + [_c_void_p] * 6,
     "epnet_attention_scale_pm": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,

@@ -29,6 +29,9 @@ int launch_transposed_gather(bool interp, bool staged_fits, int b, int c, int le
 int launch_transposed_scatter(bool interp, int b, int c, int len, long long e_total, const float *grad_out, const int *idx,
                               const float *weight, float *grad_points, cudaStream_t st);
 
+// gemm_tf32x3.cu: device address (current device) of the FP16-split range-guard flag every activation-writing epilogue raises
+unsigned int *gemm_overflow_flag();
+
 // Squared distance with the exact rounding sequence of the reference kernels as compiled by nvcc -O2
 // (PTX: sub,sub,mul,fma,sub,fma): d = fma(dz,dz, fma(dx,dx, dy*dy)), each difference taken as (a - b).
 // Written with intrinsics so that no compiler flag can change the contraction.

@@ -1595,6 +1595,15 @@ EPNET_API int epnet_deconv_planes_tma(int b, int h, int w, int cin, int k, int c
     return gemm_launch_tma(a, xh1, xh2, ldx, 1, (cudaStream_t)stream);
 }
 
+namespace epnet {
+// device address of the range-guard flag for kernels of other translation units that write activations (sa_first_level.cu)
+unsigned int *gemm_overflow_flag()
+{
+    void *p = nullptr;
+    return cudaGetSymbolAddress(&p, g_gemm_overflow) == cudaSuccess ? static_cast<unsigned int *>(p) : nullptr;
+}
+}  // namespace epnet
+
 // FP16-split range guard (see g_gemm_overflow): asynchronous read of the per-device flag into host memory (pinned for a truly
 // asynchronous copy) and reset, both ordered on `stream`.  No reference counterpart: the reference computes in fp32.
 EPNET_API int epnet_gemm_overflow_read(unsigned int *host_dst, void *stream)

@@ -263,6 +263,39 @@ def grouped_first_layer(lin, xyz, new_xyz, feats_pm, idx, relu=True, pool=1, out
     return out
 
 
+class FusedFirstLevel:
+    """One scale of a set-abstraction level WITHOUT input features in one kernel (csrc/sa_first_level.cu): group, re-centre, the
+    three shared-MLP layers (BatchNorm folded) and the max over the ball, activations in registers, plain fp32 fma.  Built from the
+    level's three PackedLinear layers; only the widths of the published configuration are instantiated."""
+    SUPPORTED = {(16, 16, 32, 16), (32, 32, 64, 32)}  # (N1, N2, N3, nsample)
+
+    @staticmethod
+    def supports(lins, nsample):
+        return (len(lins) == 3 and lins[0].K == 3 and lins[1].K == lins[0].N and lins[2].K == lins[1].N and
+                (lins[0].N, lins[1].N, lins[2].N, nsample) in FusedFirstLevel.SUPPORTED)
+
+    def __init__(self, lins, nsample):
+        assert FusedFirstLevel.supports(lins, nsample)
+        self.ns = nsample
+        self.widths = (lins[0].N, lins[1].N, lins[2].N)
+        dev = lins[0]._w.device
+        parts = []
+        for i, lin in enumerate(lins):
+            w = lin._w
+            if i == 0:
+                w = torch.cat([w, torch.zeros(w.shape[0], 1, device=dev)], dim=1)  # rows of 4: one 128-bit word per output
+            parts += [w.reshape(-1), lin.bias if lin.bias is not None else torch.zeros(lin.N, device=dev)]
+        self.pack = torch.cat(parts).contiguous()
+
+    def __call__(self, xyz, new_xyz, idx, out):
+        """xyz (B,n,3), new_xyz (B,m,3), idx (B,m,ns) int32 -> out (B*m, N3) (row stride = out.stride(0), column stride 1)"""
+        B, n, m = xyz.shape[0], xyz.shape[1], new_xyz.shape[1]
+        assert idx.shape == (B, m, self.ns) and out.shape == (B * m, self.widths[2]) and out.stride(1) == 1
+        pc._call("sa_first_level", LIB.epnet_sa_first_level, xyz, B, n, m, self.ns, *self.widths, xyz.data_ptr(), new_xyz.data_ptr(),
+                 idx.data_ptr(), self.pack.data_ptr(), out.data_ptr(), out.stride(0))
+        return out
+
+
 class PackedDeconv:
     """ConvTranspose2d with kernel == stride on NHWC activations: one GEMM per map whose epilogue writes each input pixel's
     k x k x Cout patch into the output image (csrc/gemm_tf32x3.cu, dk mode).  weight (Cin, Cout, k, k) [+ bias (Cout)]."""

@@ -176,7 +176,7 @@ class Pointnet2MSG(nn.Module):
             self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(c.fp_mlps[k])))
 
     def make_runner(self, batch, npoints, device, image_hw=(384, 1280), use_graph=True, pipeline=1, f16=True, sparse_tail=True,
-                    prefix_fps=True):
+                    prefix_fps=True, fused_first_level=True):
         """Inference fast path (eval mode): one CUDA graph with the FPS chain, the image stream and the point
         stream on parallel branches, BatchNorm folded, fused group/pool/interpolate kernels.  See runner.py.
         f16=False keeps every GEMM on the TF32 operand split (fp32 range; see BackboneRunner); sparse_tail=False evaluates the final
@@ -184,9 +184,9 @@ class Pointnet2MSG(nn.Module):
         from .runner import BackboneRunner, PipelinedRunner
         if pipeline > 1:
             return PipelinedRunner(self, batch, npoints, device, depth=pipeline, image_hw=image_hw, use_graph=use_graph, f16=f16,
-                                   sparse_tail=sparse_tail, prefix_fps=prefix_fps)
+                                   sparse_tail=sparse_tail, prefix_fps=prefix_fps, fused_first_level=fused_first_level)
         return BackboneRunner(self, batch, npoints, device, image_hw=image_hw, use_graph=use_graph, f16=f16, sparse_tail=sparse_tail,
-                              prefix_fps=prefix_fps)
+                              prefix_fps=prefix_fps, fused_first_level=fused_first_level)
 
     @staticmethod
     def _break_up_pc(pc):

@@ -20,7 +20,7 @@ import torch
 from . import image_prep
 from . import pointnet2_cuda as pc
 from .sparse_tail import SparseImageTail
-from .gemm import OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
+from .gemm import FusedFirstLevel, OverflowFlag, PackedConv3x3, PackedDeconv, PackedLinear, f16_split, grouped_first_layer, tile_policy
 
 
 class _nvtx:
@@ -93,7 +93,7 @@ class _FusionPM:
 
 class BackboneRunner:
     def __init__(self, model, batch, npoints, device, image_hw=(384, 1280), use_graph=True, tiles="latency", f16=True, sparse_tail=True,
-                 prefix_fps=True):
+                 prefix_fps=True, fused_first_level=True):
         """Point-major activations + tcgen05 fp32-grade GEMMs.
         f16: the wide GEMM tiles split operands into two FP16 terms (gemm.F16_WIDE), which needs activations and folded weights
         below 65504 in magnitude (they are below 10 for the published configuration).  Guarded twice: a layer whose folded
@@ -110,6 +110,11 @@ class BackboneRunner:
         # (csrc/fps.cu: epnet_fps_prefix_check) proves that their answer is the identity prefix -- or, on a tie, lets the sampling
         # kernels run; bit-exact either way.  False always runs the sampling kernels.
         self.prefix_fps = bool(prefix_fps)
+        # fused_first_level: a set-abstraction scale without input features (level 1 of the published configuration) runs as ONE
+        # kernel -- group, three-layer MLP in registers, max over the ball (csrc/sa_first_level.cu) -- instead of three tcgen05 GEMM
+        # launches whose tiles are all fixed cost at K <= 32; False keeps the GEMM path
+        self.fused_first_level = bool(fused_first_level)
+        self._fused_sa = {}
         self.image_hw = tuple(image_hw)
         self.overflow = OverflowFlag(device)
         self._last_stream = None
@@ -379,6 +384,16 @@ class BackboneRunner:
                         bidx = torch.zeros((B, npoint, ns), dtype=torch.int32, device=dev)
                         pc.ball_query_wrapper(B, n, npoint, radius, ns, new_xyz, xyz, bidx)
                     fpm = None if feats is None else feats.view(B, n, cin)
+                    if feats is None and self.fused_first_level and FusedFirstLevel.supports(lins, ns):
+                        if (k, si) not in self._fused_sa:
+                            self._fused_sa[(k, si)] = FusedFirstLevel(lins, ns)
+                        self._fused_sa[(k, si)](xyz, new_xyz, bidx, cat[:, c_off:c_off + lins[-1].N])
+                        if st is not main:
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            joins.append(ev)
+                        c_off += lins[-1].N
+                        continue
                     # first layer: the grouped rows go from the feature table straight into the tensor-core operand
                     x = grouped_first_layer(lins[0], xyz, new_xyz, fpm, bidx, relu=True) if len(lins) > 1 else None
                     rest = lins[1:-1]

@@ -38,6 +38,9 @@ const char *epnet_error_string(int code);
  * including which of several equally distant points wins. */
 int epnet_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream);
 
+/* The channel-major gather / group / interpolate entry points below and their gradients may take a scratch table of B*N*C floats from
+ * the library's own stream-ordered pool (cudaMallocFromPoolAsync / cudaFreeAsync on `stream`; csrc/transposed_rows.cu) when the
+ * problem is large enough for the point-major path; nothing else in this header allocates. */
 /* replaces gather_points_kernel_launcher_fast (sampling_gpu.h:12): out[b,c,j] = points[b,c,idx[b,j]] */
 int epnet_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out, void *stream);
 /* replaces gather_points_grad_kernel_launcher_fast (sampling_gpu.h:19); grad_points arrives zeroed */
@@ -103,6 +106,14 @@ int epnet_fps_sample(int b, int n, int m, const float *xyz, float *temp, int *id
 int epnet_fps_prefix_check(int b, int n, int m, const float *xyz, float *winners, int *flag, void *stream);
 int epnet_fps_sample_guarded(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, const float *aux_in,
                              float *aux_out, int aux_dim, const int *identity, void *stream);
+
+/* One scale of a set-abstraction level without input features, in one launch: QueryAndGroup (re-centred coordinates only) +
+ * SharedMLP (three 1x1 convolutions, BatchNorm(eval) folded, ReLU) + max over nsample
+ * (pointnet2_modules.py:44-58, pointnet2_utils.py:241-264, pytorch_utils.py:20-32).  pack = [W1 (n1 x 4, last column 0) | b1 |
+ * W2 (n2 x n1) | b2 | W3 (n3 x n2) | b3] floats, 16-byte aligned; out (B*m, n3) with row stride ldo.  Instantiated for
+ * (n1, n2, n3, nsample) = (16,16,32,16) and (32,32,64,32); anything else returns EPNET_ERR_BAD_ARG (use the GEMM entry points). */
+int epnet_sa_first_level(int b, int n, int m, int nsample, int n1, int n2, int n3, const float *xyz, const float *new_xyz,
+                         const int *idx, const float *pack, float *out, int ldo, void *stream);
 
 /* QueryAndGroup.forward minus the ball query (pointnet2_utils.py:250-257) in one launch:
  *   out (B,3+C,M,ns): rows 0..2 = xyz[idx] - new_xyz (re-centred coordinates), rows 3.. = features[:, idx].

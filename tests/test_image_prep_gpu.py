@@ -85,3 +85,38 @@ def test_backbone_from_decoded_image_equals_backbone_from_prepared_tensor(pipeli
         _, f_m1 = model(d["points"], d["image"], d["xy"].clone())
         _, f_m2 = model(d["points"], d["image_u8"], d["xy"].clone())
     assert torch.equal(f_m1, f_m2)
+
+
+@pytest.mark.parametrize("pipeline", [1, 3])
+def test_backbone_from_ragged_decoded_frames(pipeline):
+    """KITTI frames differ in size by a few pixels (kitti_dataset.py:44-55 pads each to the 384x1280 canvas on its own): a batch of
+    frames of different sizes in one uint8 buffer + `sizes` must give the features of the per-frame host preparation, bit for bit,
+    through the runner and through a pipelined slot."""
+    from epnet_b200 import BackboneConfig, Pointnet2MSG, scenes
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = Pointnet2MSG(config=BackboneConfig()).cuda().eval()
+    runner = model.make_runner(2, 16384, torch.device("cuda"), pipeline=pipeline)
+    host = scenes.batch(1300, 2, 16384, with_u8=True)
+    frames = host["image_u8"].numpy()
+    sizes = np.array([[375, 1242], [370, 1224]], dtype=np.int32)
+    buf = np.full_like(frames, 255)  # whatever lies outside a frame's own size must not reach the canvas
+    for i, (h, w) in enumerate(sizes):
+        buf[i, :h, :w] = frames[i, :h, :w]
+    prepared = torch.from_numpy(oracle.image_prep([frames[i, :h, :w] for i, (h, w) in enumerate(sizes)]))
+
+    def run(image, **kw):
+        out = runner(host["points"].cuda(), image, host["xy"].cuda(), **kw)
+        if pipeline > 1:
+            runner.join()
+        torch.cuda.synchronize()
+        return [t.clone() for t in out]
+
+    xyz_a, f_a = run(prepared.cuda())
+    xyz_b, f_b = run(torch.from_numpy(buf).cuda(), sizes=torch.from_numpy(sizes).cuda())
+    assert torch.equal(xyz_a, xyz_b) and torch.equal(f_a, f_b)
+    xyz_c, f_c = run(torch.from_numpy(buf).pin_memory(), sizes=torch.from_numpy(sizes))  # host buffers: staged by the runner
+    assert torch.equal(f_a, f_c)
+    _, f_d = run(torch.from_numpy(buf).cuda())  # without sizes the 255 padding is part of the frames: a different image
+    assert not torch.equal(f_a, f_d)
