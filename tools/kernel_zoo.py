@@ -56,6 +56,25 @@ for _ in range(reps):
     xy = (torch.rand(1, n, 2, generator=g) * 2 - 1).to(dev)
     og = torch.empty(1, 128, n, device=dev)
     pc.grid_gather_bilinear_wrapper(1, 128, 384, 1280, n, fmap, xy, False, og)
+    # --- round 2: gradients through the point-major scratch (red.v4), prefix check of the FPS chain, fused first level
+    gpg = torch.zeros(1, C, N, device=dev)
+    pc.group_points_grad_wrapper(1, C, N, M, ns, out_cm, gi, gpg)
+    gkn = torch.zeros(1, C2, m, device=dev)
+    pc.three_interpolate_grad_wrapper(1, C2, n, m, o_cm, idx3, w, gkn)
+    del gpg, gkn
+    flag = torch.empty(B, dtype=torch.int32, device=dev)
+    pc.fps_prefix_check_wrapper(B, 4096, 1024, new_xyz, torch.empty(B, 1024, device=dev), flag)
+    pc.fps_sample_guarded_wrapper(B, 4096, 1024, new_xyz, torch.full((B, 4096), 1e10, device=dev),
+                                  torch.empty(B, 1024, dtype=torch.int32, device=dev), flag, torch.empty(B, 1024, 3, device=dev))
+    from epnet_b200.gemm import FusedFirstLevel
+    for widths, nsf, rad in (((32, 32, 64), 32, 0.5), ((16, 16, 32), 16, 0.1)):
+        lins, kk = [], 3
+        for nn_ in widths:
+            lins.append(PackedLinear(torch.randn(nn_, kk, device=dev) / kk ** 0.5, torch.zeros(nn_, device=dev)))
+            kk = nn_
+        bq = torch.zeros(B, 4096, nsf, dtype=torch.int32, device=dev)
+        pc.ball_query_wrapper(B, 16384, 4096, rad, nsf, new_xyz, pts, bq)
+        FusedFirstLevel(lins, nsf)(pts, new_xyz, bq, torch.empty(B * 4096, widths[2], device=dev))
     x = torch.randn(2, 64, 491520, device=dev)
     pc.bias_relu_wrapper(2, 64, 491520, x, torch.randn(64, device=dev))
     # --- tcgen05 GEMM at a large shared-MLP shape and with the pooled epilogue
