@@ -153,7 +153,10 @@ class BackboneRunner:
 
             self._build_pm()
 
-        self.s_fps = torch.cuda.Stream(device=device)
+        # the FPS chain is the critical path of a batch and needs a whole SM's shared memory per scene: high priority, so that its CTAs
+        # are placed as soon as an SM drains instead of queueing behind the image stream's grids (one batch at a time: 2.98 -> 2.90 ms;
+        # throughput with 8 batches in flight unchanged)
+        self.s_fps = torch.cuda.Stream(device=device, priority=-1)
         self.s_img = torch.cuda.Stream(device=device)
         self.s_scale = [torch.cuda.Stream(device=device)]  # second grouping scale of a set-abstraction level
         self.s_geo = [torch.cuda.Stream(device=device) for _ in range(3)]  # geometry-only work: ball queries (2 scales), three_nn
