@@ -67,6 +67,36 @@ for name, h2d, d2h, key in rows:
     ms = run(h2d, d2h, key)
     if rank == 0:
         print("%d GPU(s)  %-46s %.4f ms/step  %.1f scenes/s" % (world, name, ms, 2 * world / ms * 1e3), flush=True)
+
+
+def copy_rate(direction, mb=17.17, reps=40):
+    """the link alone: `reps` pinned copies of one step's result size, all ranks at once -> GB/s per GPU (slowest rank) and in aggregate"""
+    n = int(mb * 1e6 / 4)
+    d = torch.empty(n, device=dev)
+    h = torch.empty(n).pin_memory()
+    src, dst = (d, h) if direction == "d2h" else (h, d)
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    sync_ranks()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gbs = reps * n * 4 / (t.item() * 1e-3) / 1e9
+    if rank == 0:
+        print("%d GPU(s)  %s alone, %.2f MB pinned copies on every rank at once: %.1f GB/s per GPU, %.1f GB/s in aggregate (%.3f ms per copy)" %
+              (world, direction.upper(), mb, gbs, gbs * world, t.item() / reps), flush=True)
+
+
+copy_rate("d2h")
+copy_rate("h2d", mb=3.45)
+copy_rate("h2d", mb=12.45)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
