@@ -279,12 +279,10 @@ class FusedFirstLevel:
         self.ns = nsample
         self.widths = (lins[0].N, lins[1].N, lins[2].N)
         dev = lins[0]._w.device
-        parts = []
-        for i, lin in enumerate(lins):
-            w = lin._w
-            if i == 0:
-                w = torch.cat([w, torch.zeros(w.shape[0], 1, device=dev)], dim=1)  # rows of 4: one 128-bit word per output
-            parts += [w.reshape(-1), lin.bias if lin.bias is not None else torch.zeros(lin.N, device=dev)]
+        bias = [lin.bias if lin.bias is not None else torch.zeros(lin.N, device=dev) for lin in lins]
+        # layout of csrc/sa_first_level.cu SaPack: W1 rows (wx, wy, wz, bias) | W2 transposed (k-major) | b2 | W3 | b3
+        parts = [torch.cat([lins[0]._w, bias[0][:, None]], dim=1).reshape(-1), lins[1]._w.t().contiguous().reshape(-1), bias[1],
+                 lins[2]._w.reshape(-1), bias[2]]
         self.pack = torch.cat(parts).contiguous()
 
     def __call__(self, xyz, new_xyz, idx, out):

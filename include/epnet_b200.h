@@ -109,8 +109,8 @@ int epnet_fps_sample_guarded(int b, int n, int m, const float *xyz, float *temp,
 
 /* One scale of a set-abstraction level without input features, in one launch: QueryAndGroup (re-centred coordinates only) +
  * SharedMLP (three 1x1 convolutions, BatchNorm(eval) folded, ReLU) + max over nsample
- * (pointnet2_modules.py:44-58, pointnet2_utils.py:241-264, pytorch_utils.py:20-32).  pack = [W1 (n1 x 4, last column 0) | b1 |
- * W2 (n2 x n1) | b2 | W3 (n3 x n2) | b3] floats, 16-byte aligned; out (B*m, n3) with row stride ldo.  Instantiated for
+ * (pointnet2_modules.py:44-58, pointnet2_utils.py:241-264, pytorch_utils.py:20-32).  pack = [W1 (n1 rows of wx, wy, wz, bias) |
+ * W2 transposed (n1 x n2) | b2 | W3 (n3 x n2) | b3] floats, 16-byte aligned; out (B*m, n3) with row stride ldo.  Instantiated for
  * (n1, n2, n3, nsample) = (16,16,32,16) and (32,32,64,32); anything else returns EPNET_ERR_BAD_ARG (use the GEMM entry points). */
 int epnet_sa_first_level(int b, int n, int m, int nsample, int n1, int n2, int n3, const float *xyz, const float *new_xyz,
                          const int *idx, const float *pack, float *out, int ldo, void *stream);
