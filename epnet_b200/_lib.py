@@ -68,6 +68,7 @@ SIGNATURES = {
     "epnet_tail_blend": [_c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p],
     "epnet_gemm_tf32x3_rows": [_c_int] * 3 + [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                _c_void_p, _c_int, _c_void_p],
+    "epnet_conv3x3_c3_planes": [_c_int] * 4 + [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p],
     "epnet_image_prep_u8": [_c_int] * 3 + [_c_ll, _c_ll, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
     "epnet_image_nchw_to_nhwc4": [_c_int] * 3 + [_c_void_p, _c_void_p, _c_void_p],
     "epnet_gemm_overflow_read": [_c_void_p, _c_void_p],

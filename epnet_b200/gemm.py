@@ -338,6 +338,9 @@ class PackedConv3x3:
         wp[..., :cin] = w.permute(0, 2, 3, 1)
         self.lin = PackedLinear(wp.reshape(cout, 9 * cin_p), bias)
         self.cin, self.cin_p, self.cout, self.stride = cin, cin_p, cout, stride
+        # 3 -> 64 channels, stride 1 (the first convolution of the image stream): K = 27 is too short for a tensor-core tile; a dedicated
+        # fp32 FFMA kernel (csrc/first_conv.cu) takes the (o, ky, kx, c) weights as they are
+        self.w_c3 = wp.contiguous() if (cin == 3 and cout == 64 and stride == 1) else None
 
     def planes_capable(self):
         """can this layer read its input as FP16 planes through TMA (k-blocks of one tap x 64 channels; weights inside fp16's range)?"""
@@ -365,6 +368,11 @@ class PackedConv3x3:
             assert out.stride(-1) == 1 and out.stride(-3) == Wo * out.stride(-2) and out.stride(0) == Ho * out.stride(-3)
         ph1 = None if planes is None else planes.h1.data_ptr()
         ph2 = None if planes is None else planes.h2.data_ptr()
+        if self.w_c3 is not None and not isinstance(x, Planes) and W % 4 == 0 and (out is None or (out.stride(-2) % 4 == 0 and out.data_ptr() % 16 == 0)):
+            pc._call("conv3x3_c3_planes", LIB.epnet_conv3x3_c3_planes, x, B, H, W, self.cout, x.data_ptr(), self.w_c3.data_ptr(),
+                     None if lin.bias is None else lin.bias.data_ptr(), int(bool(relu)), None if out is None else out.data_ptr(),
+                     0 if out is None else out.stride(-2), ph1, ph2, self.cout)
+            return (out, planes) if planes_out else out
         if isinstance(x, Planes):
             bn = tma_bn(self.cout, B * Ho * Wo)
             pc._call("conv3x3_planes_tma", LIB.epnet_conv3x3_planes_tma, x.h1, B, H, W, self.cin_p, self.cout, self.stride, x.h1.data_ptr(),

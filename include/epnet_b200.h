@@ -218,6 +218,13 @@ int epnet_gemm_tf32x3_rows(int L, int K, int N, const float *x, int ldx, const i
                            const int *m_tiles_dev, const float *wpack, int BN, const float *bias, int relu, float *y, int ldy,
                            void *stream);
 
+/* The FIRST convolution of the image stream (Img_Block[0].conv1 + folded BatchNorm + ReLU, /root/reference/lib/net/pointnet2_msg.py:17-24: 3 -> 64
+ * channels, 3x3, stride 1, pad 1) as a dedicated fp32 FFMA kernel: K = 27 is too short for the tensor-core tile.  x (b,H,W,4) fp32 NHWC, channel 3
+ * ignored; w (64,3,3,4) = (o,ky,kx,c); bias (64) or NULL; outputs y (b*H*W, ldy) fp32 and/or FP16 planes yh1/yh2 (b*H*W, ldh) for a following
+ * *_planes_tma layer (either may be NULL, not both).  cout must be 64, W a multiple of 4. */
+int epnet_conv3x3_c3_planes(int b, int H, int W, int cout, const float *x, const float *w, const float *bias, int relu, float *y, int ldy,
+                            void *yh1, void *yh2, int ldh, void *stream);
+
 /* Range guard of the FP16 operand split (no reference counterpart: pytorch_utils.py:20-32 computes in fp32).  Every GEMM
  * epilogue of this library raises a per-device flag when it writes a magnitude above 6e4 or a non-finite value -- i.e. whenever
  * a following FP16-split layer could overflow.  _read copies the flag (0/1) to host memory asynchronously on `stream` (pinned

@@ -51,6 +51,35 @@ def test_conv_from_planes_matches_float64(cin, cout, stride, hw):
     assert only_planes[0] is None and torch.equal(only_planes[1].h1, py.h1) and torch.equal(only_planes[1].h2, py.h2)
 
 
+def test_first_conv_ffma_kernel_matches_float64():
+    """3 -> 64 channels, stride 1: the dedicated fp32 FFMA kernel (csrc/first_conv.cu), fp32 and planes outputs, borders included"""
+    from epnet_b200.gemm import PackedConv3x3
+    g = torch.Generator().manual_seed(11)
+    for (H, W) in ((32, 64), (17, 36), (384, 1280)):
+        x = torch.zeros(2, H, W, 4)
+        x[..., :3] = torch.randn(2, H, W, 3, generator=g)
+        x[..., 3] = 123.0  # the padded channel is ignored
+        x = x.cuda()
+        w = (torch.randn(64, 3, 3, 3, generator=g) / 5).cuda()
+        bias = torch.randn(64, generator=g).cuda()
+        conv = PackedConv3x3(w, bias, stride=1)
+        assert conv.w_c3 is not None
+        y, p = conv(x, relu=True, planes_out=True)
+        _, p_only = conv(x, relu=True, planes_out=True, f32_out=False)
+        y_only = conv(x, relu=True)
+        torch.cuda.synchronize()
+        want = F.relu(F.conv2d(x[..., :3].double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)).permute(0, 2, 3, 1)
+        assert _rel(y, want) <= 1e-6, _rel(y, want)  # plain fp32 accumulation of 27 products
+        assert torch.equal(y, y_only)
+        assert (p.float() - y).abs().max().item() <= 2.0 ** -21 * y.abs().max().item()
+        assert torch.equal(p.h1, p_only.h1) and torch.equal(p.h2, p_only.h2)
+    # a width that is not a multiple of 4 stays on the tensor-core path
+    x = torch.randn(1, 9, 38, 4).cuda()
+    y = conv(x, relu=True)
+    want = F.relu(F.conv2d(x[..., :3].double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)).permute(0, 2, 3, 1)
+    assert _rel(y, want) <= TOL
+
+
 def test_first_conv_writes_planes_and_chain_matches():
     from epnet_b200.gemm import PackedConv3x3
     g = torch.Generator().manual_seed(5)
