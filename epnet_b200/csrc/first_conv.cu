@@ -6,11 +6,12 @@
 // im2col operand materialised by the preparation kernel 114 + 166 us (the 252 MB operand is written and read once more).
 // A first SIMT version (two pixels x 64 channels per thread) measured 205 us: a broadcast 128-bit shared-memory load occupies the
 // load/store write-back path for four cycles -- 16 FFMA issue slots -- and it fed only 8 FFMAs; and every thread wrote its pixels'
-// 128-byte plane rows alone, one line per lane and store.  This version: a thread owns FOUR horizontally adjacent pixels and 16 of
-// the 64 output channels (the four lanes of a quad share the pixels and split the channels), so one weight word (4 channels of one
-// k) feeds 16 FFMAs, the four lanes' weight words are one multicast shared-memory access, and a quad's stores of one pixel fill one
-// half of a 128-byte line of each plane together (whole sectors).  Plain FFMA (exact fp32 accumulation, bias first, k ascending: ky, kx, c); the epilogue
-// writes the two FP16 planes the next convolution reads with TMA (x = h1 + 2^-11 h2) and/or fp32 NHWC.
+// 128-byte plane rows alone, one line per lane and store.  This version: a thread owns EIGHT horizontally adjacent pixels and 8 of
+// the 64 output channels (the eight lanes of a group share the pixels and split the channels), so one weight word (4 channels of one
+// k) feeds 32 FFMAs, the eight lanes' weight words are one 128-byte multicast shared-memory access, and a group's store of one pixel
+// is one whole 128-byte row of a plane.  (Four pixels x 16 channels: 117 us; this: 111 us.)  Plain FFMA (exact fp32 accumulation,
+// bias first, k ascending: ky, kx, c); the epilogue writes the two FP16 planes the next convolution reads with TMA
+// (x = h1 + 2^-11 h2) and/or fp32 NHWC.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -18,8 +19,9 @@ namespace epnet {
 
 constexpr int kFcThreads = 128;
 constexpr int kFcCout = 64;
-constexpr int kFcPix = 4;     // pixels per thread
-constexpr int kFcChunk = 16;  // output channels per thread
+constexpr int kFcPix = 8;     // pixels per thread
+constexpr int kFcChunk = 8;   // output channels per thread
+constexpr int kFcLanes = kFcCout / kFcChunk;  // lanes sharing a pixel group: 8
 
 __device__ __forceinline__ void fc_split2(float a, float b, uint32_t &h1, uint32_t &h2)
 {
@@ -31,7 +33,7 @@ __device__ __forceinline__ void fc_split2(float a, float b, uint32_t &h1, uint32
     h2 = *reinterpret_cast<const uint32_t *>(&q);
 }
 
-constexpr int kFcTilePix = kFcThreads / 4 * kFcPix;  // 128 pixels of one image row per CTA and trip
+constexpr int kFcTilePix = kFcThreads / kFcLanes * kFcPix;  // 128 pixels of one image row per CTA and trip
 constexpr int kFcTileCols = kFcTilePix + 2;           // + the left and right halo column
 
 __device__ __forceinline__ void fc_cp_async16(void *dst_smem, const void *src)
@@ -46,25 +48,24 @@ __global__ void __launch_bounds__(kFcThreads, 4)
 first_conv_kernel(int b, int H, int W, const float4 *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int relu,
                   float *__restrict__ y, int ldy, uint4 *__restrict__ yh1, uint4 *__restrict__ yh2, int ldh, unsigned int *__restrict__ overflow)
 {
-    // the 27 x 64 weights, K-major; a thread (channel chunk ck) owns channels 8 ck .. 8 ck + 7 and 32 + 8 ck .. 32 + 8 ck + 7, so that the four
-    // lanes of a quad write 64 contiguous bytes (two whole sectors) of a plane row per store instruction.  w_s[k][o4][ck][e] holds channel
-    // 32 (o4 / 2) + 8 ck + 4 (o4 % 2) + e: the words the four lanes read in the same instruction are adjacent -- 64 contiguous bytes per
-    // warp, one conflict-free multicast access (with [k][o] order chunks 0/2 and 1/3 hit the same banks: 177 us instead of 152)
+    // the 27 x 64 weights, K-major; a thread (channel chunk ck of 8) owns channels 8 ck .. 8 ck + 7, i.e. 16 bytes of a plane row: the eight
+    // lanes of a pixel group write one whole 128-byte row per store instruction.  w_s[k][o4][ck][e] holds channel 8 ck + 4 o4 + e: the words the
+    // eight lanes read in the same instruction are adjacent -- 128 contiguous bytes per warp, one conflict-free multicast access
     __shared__ __align__(16) float w_s[27 * kFcCout];
     __shared__ __align__(16) float b_s[kFcCout];
     __shared__ __align__(16) float4 tile[2][3][kFcTileCols + 2];
     for (int i = threadIdx.x; i < 27 * kFcCout; i += kFcThreads) {
         const int k = i / kFcCout, r = i - k * kFcCout;
-        const int o4 = r >> 4, ck = (r >> 2) & 3, e = r & 3;
-        const int o = 32 * (o4 >> 1) + 8 * ck + 4 * (o4 & 1) + e;
+        const int o4 = r >> 5, ck = (r >> 2) & 7, e = r & 3;
+        const int o = 8 * ck + 4 * o4 + e;
         const int tap = k / 3, c = k - 3 * tap;
         w_s[i] = __ldg(w + ((size_t)o * 9 + tap) * 4 + c);  // w: (64, 3, 3, 4) = (o, ky, kx, c padded to 4)
     }
     if (threadIdx.x < kFcCout) {
-        const int r = threadIdx.x, o4 = r >> 4, ck = (r >> 2) & 3, e = r & 3;
-        b_s[r] = bias ? __ldg(bias + 32 * (o4 >> 1) + 8 * ck + 4 * (o4 & 1) + e) : 0.f;
+        const int r = threadIdx.x, o4 = r >> 5, ck = (r >> 2) & 7, e = r & 3;
+        b_s[r] = bias ? __ldg(bias + 8 * ck + 4 * o4 + e) : 0.f;
     }
-    const int chunk = threadIdx.x & 3, quad = threadIdx.x >> 2;
+    const int chunk = threadIdx.x & (kFcLanes - 1), quad = threadIdx.x / kFcLanes;  // quad: the pixel group of this thread
     const float *wc = w_s + chunk * 4;
     const int tiles_x = (W + kFcTilePix - 1) / kFcTilePix;
     const long long total = (long long)b * H * tiles_x;
@@ -106,7 +107,7 @@ first_conv_kernel(int b, int H, int W, const float4 *__restrict__ x, const float
         float acc[kFcPix][kFcChunk];
 #pragma unroll
         for (int o4 = 0; o4 < kFcChunk / 4; ++o4) {
-            const float4 bb = *reinterpret_cast<const float4 *>(b_s + (o4 * 4 + chunk) * 4);
+            const float4 bb = *reinterpret_cast<const float4 *>(b_s + (o4 * kFcLanes + chunk) * 4);
 #pragma unroll
             for (int p = 0; p < kFcPix; ++p) { acc[p][4 * o4] = bb.x; acc[p][4 * o4 + 1] = bb.y; acc[p][4 * o4 + 2] = bb.z; acc[p][4 * o4 + 3] = bb.w; }
         }
@@ -119,7 +120,7 @@ first_conv_kernel(int b, int H, int W, const float4 *__restrict__ x, const float
                     const float4 *wk = reinterpret_cast<const float4 *>(wc + ((dy * 3 + dx) * 3 + ch) * kFcCout);
 #pragma unroll
                     for (int o4 = 0; o4 < kFcChunk / 4; ++o4) {
-                        const float4 ww = wk[4 * o4];  // four adjacent words per warp (one per channel chunk): one multicast access
+                        const float4 ww = wk[kFcLanes * o4];  // adjacent words per warp (one per channel chunk): one multicast access
 #pragma unroll
                         for (int p = 0; p < kFcPix; ++p) {
                             const float a = in[dy][p + dx][ch];  // tap (dy, dx) of pixel p
@@ -132,33 +133,27 @@ first_conv_kernel(int b, int H, int W, const float4 *__restrict__ x, const float
                 }
             }
         }
-        // acc[p][0..7] = channels 8 chunk .. +7, acc[p][8..15] = channels 32 + 8 chunk .. +7
+        // acc[p][0..7] = channels 8 chunk .. 8 chunk + 7
         const size_t pix = ((size_t)s * H + yy) * W + x0;
 #pragma unroll
         for (int p = 0; p < kFcPix; ++p) {
+            if (x0 + p >= W) break;  // W is a multiple of 4, a pixel group has 8: the last group of a row may be half empty
 #pragma unroll
             for (int o = 0; o < kFcChunk; ++o) {
                 if (relu) acc[p][o] = fmaxf(acc[p][o], 0.f);
                 amax = fmaxf(amax, fabsf(acc[p][o]));
             }
             if (y) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float4 *d = reinterpret_cast<float4 *>(y + (pix + p) * ldy + 32 * g + 8 * chunk);
-                    __stcs(d, make_float4(acc[p][8 * g], acc[p][8 * g + 1], acc[p][8 * g + 2], acc[p][8 * g + 3]));
-                    __stcs(d + 1, make_float4(acc[p][8 * g + 4], acc[p][8 * g + 5], acc[p][8 * g + 6], acc[p][8 * g + 7]));
-                }
+                float4 *d = reinterpret_cast<float4 *>(y + (pix + p) * ldy + 8 * chunk);
+                __stcs(d, make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]));
+                __stcs(d + 1, make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]));
             }
-            if (yh1) {  // 8 channels = 16 bytes per store; the four lanes of the quad write 64 contiguous bytes of the plane row together
-                uint4 *d1 = yh1 + (pix + p) * (ldh >> 3) + chunk, *d2 = yh2 + (pix + p) * (ldh >> 3) + chunk;
+            if (yh1) {  // 8 channels = 16 bytes per plane: the eight lanes of the group write the whole 128-byte row together
+                uint32_t a1[4], a2[4];
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint32_t a1[4], a2[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) fc_split2(acc[p][8 * g + 2 * e], acc[p][8 * g + 2 * e + 1], a1[e], a2[e]);
-                    d1[4 * g] = make_uint4(a1[0], a1[1], a1[2], a1[3]);
-                    d2[4 * g] = make_uint4(a2[0], a2[1], a2[2], a2[3]);
-                }
+                for (int e = 0; e < 4; ++e) fc_split2(acc[p][2 * e], acc[p][2 * e + 1], a1[e], a2[e]);
+                yh1[(pix + p) * (ldh >> 3) + chunk] = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+                yh2[(pix + p) * (ldh >> 3) + chunk] = make_uint4(a2[0], a2[1], a2[2], a2[3]);
             }
         }
         }
@@ -176,7 +171,7 @@ EPNET_API int epnet_conv3x3_c3_planes(int b, int H, int W, int cout, const float
                                       int ldy, void *yh1, void *yh2, int ldh, void *stream)
 {
     using namespace epnet;
-    if (b < 0 || H <= 0 || W <= 0 || (W % kFcPix) || cout != kFcCout || !x || !w || (!y && !yh1)) return EPNET_ERR_BAD_ARG;
+    if (b < 0 || H <= 0 || W <= 0 || (W % 4) || cout != kFcCout || !x || !w || (!y && !yh1)) return EPNET_ERR_BAD_ARG;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (y && (ldy < cout || (ldy & 3) || (reinterpret_cast<uintptr_t>(y) & 15)))) return EPNET_ERR_BAD_ARG;
     if (yh1 && (!yh2 || ldh < cout || (ldh & 7) || ((reinterpret_cast<uintptr_t>(yh1) | reinterpret_cast<uintptr_t>(yh2)) & 15))) return EPNET_ERR_BAD_ARG;
     if (b == 0) return EPNET_OK;
