@@ -85,3 +85,57 @@ def test_weight_packing_layouts_on_cpu():
     assert (back[:200, :99] - w).abs().max() <= w.abs().max() * 2.0 ** -21
     assert back[200:].abs().max() == 0 and back[:, 99:].abs().max() == 0
     assert full16.shape[2] % 64 == 0 and full.shape[2] % 32 == 0
+
+
+def test_round2_entry_points_validate_before_launching():
+    """argument checks of the entry points added in round 2 (no device is touched)"""
+    from epnet_b200 import _lib
+    lib = _lib.LIB
+    p = ctypes.c_void_p(4096)
+    bad = _lib.EPNET_ERR_BAD_ARG if hasattr(_lib, "EPNET_ERR_BAD_ARG") else -1
+    assert lib.epnet_sa_first_level(2, 16384, 4096, 32, 32, 32, 128, p, p, p, p, p, 128, None) == bad   # widths not instantiated
+    assert lib.epnet_sa_first_level(2, 16384, 4096, 16, 32, 32, 64, p, p, p, p, p, 64, None) == bad     # nsample / width mismatch
+    assert lib.epnet_sa_first_level(2, 16384, 4096, 32, 32, 32, 64, p, p, p, p, p, 32, None) == bad     # ldo < n3
+    assert lib.epnet_sa_first_level(2, 16384, 4096, 32, 32, 32, 64, p, p, p, ctypes.c_void_p(4100), p, 64, None) == bad  # pack not 16-byte aligned
+    assert lib.epnet_conv3x3_c3_planes(2, 384, 1282, 64, p, p, None, 1, p, 64, None, None, 0, None) == bad   # W % 4 != 0
+    assert lib.epnet_conv3x3_c3_planes(2, 384, 1280, 32, p, p, None, 1, p, 64, None, None, 0, None) == bad   # cout != 64
+    assert lib.epnet_conv3x3_c3_planes(2, 384, 1280, 64, p, p, None, 1, None, 0, None, None, 0, None) == bad  # no output at all
+    assert lib.epnet_conv3x3_c3_planes(2, 384, 1280, 64, p, p, None, 1, None, 0, p, None, 64, None) == bad    # one plane without the other
+    assert lib.epnet_fps_prefix_check(2, 1024, 2048, p, p, p, None) == bad                                    # m > n
+    assert lib.epnet_fps_sample_guarded(2, 4096, 1024, p, p, p, p, None, None, 0, None, None) == bad          # no identity flags
+    assert lib.epnet_fps_sample_guarded(2, 1024, 4096, p, p, p, p, None, None, 0, p, None) == bad             # m > n
+
+
+def test_fused_first_level_pack_layout_on_cpu():
+    """gemm.FusedFirstLevel packs the three folded layers for csrc/sa_first_level.cu (SaPack): W1 rows (wx, wy, wz, bias) | W2 transposed
+    (k-major) | b2 | W3 | b3; supports() admits exactly the published first-level scales"""
+    import torch
+    from epnet_b200.gemm import FusedFirstLevel, PackedLinear
+    g = torch.Generator().manual_seed(9)
+
+    def layers(widths, first_k=3, bias=True):
+        lins, k = [], first_k
+        for n in widths:
+            lins.append(PackedLinear(torch.randn(n, k, generator=g), torch.randn(n, generator=g) if bias else None))
+            k = n
+        return lins
+
+    lins = layers((32, 32, 64))
+    assert FusedFirstLevel.supports(lins, 32) and not FusedFirstLevel.supports(lins, 16)
+    assert FusedFirstLevel.supports(layers((16, 16, 32)), 16)
+    assert not FusedFirstLevel.supports(layers((32, 32, 64), first_k=4), 32)      # a level with an input feature (intensity)
+    assert not FusedFirstLevel.supports(layers((64, 64, 128)), 32)                  # the second level's widths
+    assert not FusedFirstLevel.supports(layers((32, 32)), 32)                       # two layers
+    pack = FusedFirstLevel(lins, 32).pack
+    n1, n2, n3 = 32, 32, 64
+    assert pack.numel() == n1 * 4 + n1 * n2 + n2 + n3 * n2 + n3 and pack.data_ptr() % 16 == 0
+    o = 0
+    w1 = pack[o:o + n1 * 4].view(n1, 4); o += n1 * 4
+    assert torch.equal(w1[:, :3], lins[0]._w) and torch.equal(w1[:, 3], lins[0].bias)
+    w2t = pack[o:o + n1 * n2].view(n1, n2); o += n1 * n2
+    assert torch.equal(w2t, lins[1]._w.t())
+    assert torch.equal(pack[o:o + n2], lins[1].bias); o += n2
+    assert torch.equal(pack[o:o + n3 * n2].view(n3, n2), lins[2]._w); o += n3 * n2
+    assert torch.equal(pack[o:o + n3], lins[2].bias)
+    nb = FusedFirstLevel(layers((16, 16, 32), bias=False), 16).pack  # layers without a bias: zeros in the bias slots
+    assert nb[:64].view(16, 4)[:, 3].abs().max() == 0 and nb[64 + 256:64 + 256 + 16].abs().max() == 0
