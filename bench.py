@@ -233,14 +233,19 @@ def main():
                 return runner(b["points"], b["image"], b["xy"])
             return model(b["points"], b["image"], b["xy"].clone())  # the model normalises xy in place
 
-    out_host = [None] * depth   # pinned result buffers, one per in-flight slot
-    done = [None] * depth       # event: slot's D2H finished
+    # pinned result buffers on the host: a ring twice as deep as the device pipeline, so that the host (the consumer of the results)
+    # may lag up to 2 x depth batches behind the GPU before it has to wait -- the device-side order (replay -> D2H -> next replay of
+    # the slot) is the slot stream's; with a ring of only `depth` buffers the host could not queue batch i + depth before batch i's
+    # result had landed, and a 20-step run spent ~5 ms with an under-filled GPU queue
+    ring = 2 * depth
+    out_host = [None] * ring
+    done = [None] * ring        # event: that buffer's D2H finished
 
     def step_e2e(i):
-        slot = i % depth
+        slot = i % ring
         hb = pinned[i % len(pinned)]
         if done[slot] is not None:
-            done[slot].synchronize()  # the host consumes the result of the batch that used this slot `depth` steps ago
+            done[slot].synchronize()  # the host consumes the result of the batch that used this buffer `ring` steps ago
         if runner is not None and depth > 1:
             xyz, feats = runner(hb["points"], hb[image_key[0]], hb["xy"])  # H2D from pinned memory happens on the slot's stream
             st = runner.stream_of_last_call()
@@ -295,7 +300,7 @@ def main():
 
     # untimed e2e warm-up: every in-flight slot gets its pinned result buffers here (cudaHostAlloc synchronises the device and
     # takes milliseconds; inside the timed region it showed up as a 5-25 % run-to-run spread of e2e)
-    for i in range(max(3, depth + 1)):
+    for i in range(max(3, 2 * depth + 1)):
         step_e2e(i)
     drain()
     ms_e2e = timed_region(step_e2e, args.steps, rank_sync, drain)
