@@ -234,8 +234,9 @@ def main():
             return model(b["points"], b["image"], b["xy"].clone())  # the model normalises xy in place
 
     # pinned result buffers on the host: a ring twice as deep as the device pipeline, so that the host (the consumer of the results)
-    # may lag up to 2 x depth batches behind the GPU before it has to wait -- the device-side order (replay -> D2H -> next replay of
-    # the slot) is the slot stream's; with a ring of only `depth` buffers the host could not queue batch i + depth before batch i's
+    # may lag up to 2 x depth batches behind the GPU before it has to wait -- the device-side order (replay -> staging copy -> next
+    # replay of the slot) is the slot stream's, the transfer itself runs on the runner's copy stream (PipelinedRunner.read_back); with
+    # a ring of only `depth` buffers the host could not queue batch i + depth before batch i's
     # result had landed, and a 20-step run spent ~5 ms with an under-filled GPU queue
     ring = 2 * depth
     out_host = [None] * ring
@@ -265,6 +266,11 @@ def main():
                 xyz, feats = runner(pts, img, xy) if runner is not None else model(pts, img, xy)
         if out_host[slot] is None:
             out_host[slot] = (torch.empty(xyz.shape, dtype=xyz.dtype).pin_memory(), torch.empty(feats.shape, dtype=feats.dtype).pin_memory())
+        if runner is not None and depth > 1:
+            # device-side staging copy on the slot's stream, D2H on the runner's copy stream: the slot is free for its next batch
+            # while the result crosses the link (at 8 ranks per host a 17 MB read-back lasts as long as a step)
+            done[slot] = runner.read_back(slot, out_host[slot][0], out_host[slot][1])
+            return
         with torch.cuda.stream(st):
             out_host[slot][0].copy_(xyz, non_blocking=True)
             out_host[slot][1].copy_(feats, non_blocking=True)

@@ -552,6 +552,35 @@ class PipelinedRunner:
         self.streams = [torch.cuda.Stream(device=device) for _ in range(depth)]
         self.kernel_launches_per_replay = self.runners[0].kernel_launches_per_replay
         self.calls = 0
+        self._copy_stream = None
+        self._staging = {}
+        self._last = None
+
+    def read_back(self, key, host_xyz, host_feats):
+        """Deliver the results of the LAST call to pinned host tensors without holding its slot for the duration of the transfer:
+        a device-side copy into a staging pair (on the slot's stream, microseconds) frees the slot, the device->host copy runs
+        on a dedicated copy stream.  `key` names the staging pair (reuse a key only after the event returned for it has completed:
+        a ring of keys as deep as the host may lag).  Returns the event that marks the host tensors valid.  With eight ranks
+        sharing one host link a 17 MB read-back takes as long as a whole step; on the slot's own stream it made every slot's
+        cycle that much longer (tools/e2e_scaling_probe.py)."""
+        i = (self.calls - 1) % len(self.runners)
+        xyz, feats = self._last
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if key not in self._staging:
+            self._staging[key] = (torch.empty_like(xyz), torch.empty_like(feats))
+        sx, sf = self._staging[key]
+        st = self.streams[i]
+        with torch.cuda.stream(st):
+            sx.copy_(xyz, non_blocking=True)
+            sf.copy_(feats, non_blocking=True)
+        self._copy_stream.wait_stream(st)
+        with torch.cuda.stream(self._copy_stream):
+            host_xyz.copy_(sx, non_blocking=True)
+            host_feats.copy_(sf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return ev
 
     def __call__(self, points, image, xy, sizes=None):
         i = self.calls % len(self.runners)
@@ -559,7 +588,8 @@ class PipelinedRunner:
         st = self.streams[i]
         st.wait_stream(torch.cuda.current_stream(self.device))  # inputs produced on the caller's stream
         with torch.cuda.stream(st):
-            return self.runners[i](points, image, xy, sizes)
+            self._last = self.runners[i](points, image, xy, sizes)
+        return self._last
 
     def stream_of_last_call(self):
         return self.streams[(self.calls - 1) % len(self.runners)]
@@ -573,10 +603,12 @@ class PipelinedRunner:
         return self.runners[0].overflow
 
     def join(self):
-        """make the caller's current stream wait for every in-flight batch"""
+        """make the caller's current stream wait for every in-flight batch (and every read_back in flight)"""
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             cur.wait_stream(st)
+        if self._copy_stream is not None:
+            cur.wait_stream(self._copy_stream)
 
     def eager(self, *a, **kw):
         return self.runners[0].eager(*a, **kw)
