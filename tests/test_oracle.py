@@ -147,6 +147,49 @@ def test_fps_of_an_fps_ordered_cloud_is_the_identity_prefix():
     np.testing.assert_array_equal(again, np.broadcast_to(np.arange(256, dtype=np.int32), (2, 256)))
 
 
+def _prefix_condition(p, m):
+    """csrc/fps.cu epnet_fps_prefix_check, restated: with T_j(s) = min(1e10, d(p_j, p_0), ..., d(p_j, p_{s-1})) in the reference's fp32
+    arithmetic (the oracle's distance: fma(dz,dz, fma(dx,dx, dy*dy))), the identity 0..m-1 is certified iff T_j(s) < T_s(s) for every
+    step 1 <= s < m and every j != s."""
+    n = p.shape[0]
+    t = np.full(n, np.float32(1e10), dtype=np.float32)
+    for s in range(1, m):
+        q = p[s - 1]
+        dx, dy, dz = (p[:, 0] - q[0]).astype(np.float32), (p[:, 1] - q[1]).astype(np.float32), (p[:, 2] - q[2]).astype(np.float32)
+        # float64 products of float32 values are exact, one rounding per fma: the same chain as the kernels
+        inner = (dx.astype(np.float64) * dx + (dy * dy).astype(np.float32).astype(np.float64)).astype(np.float32)
+        d = (dz.astype(np.float64) * dz + inner).astype(np.float32)
+        t = np.minimum(d, t)
+        others = np.delete(t, s)
+        if not np.all(others < t[s]):
+            return False
+    return True
+
+
+def test_prefix_condition_certifies_exactly_the_identity():
+    """The decision rule of the FPS shortcut against the oracle's sampling: whenever the condition holds, sampling the cloud returns
+    the identity (whatever the tie rule); on clouds with ties or not in furthest-point order it must refuse, and there the oracle's
+    answer is indeed allowed to differ."""
+    from cases import cloud, lidar
+    xyz = lidar(5, 1, 2048)[0]
+    first = oracle.furthest_point_sampling(xyz[None], 512)[0]
+    ordered = xyz[first]
+    assert _prefix_condition(ordered, 128)
+    np.testing.assert_array_equal(oracle.furthest_point_sampling(ordered[None], 128)[0], np.arange(128, dtype=np.int32))
+    swapped = ordered.copy()
+    swapped[[3, 200]] = swapped[[200, 3]]
+    assert not _prefix_condition(swapped, 128)
+    assert not np.array_equal(oracle.furthest_point_sampling(swapped[None], 128)[0], np.arange(128, dtype=np.int32))
+    lat = cloud(71, 1, 1024, "lattice")[0]
+    lat_first = oracle.furthest_point_sampling(lat[None], 256)[0]
+    assert not _prefix_condition(lat[lat_first], 64)  # 216 distinct lattice points: ties from the first steps on
+    dup = ordered.copy()
+    dup[40] = dup[41]
+    assert not _prefix_condition(dup, 128)
+    # and the subset property the runner relies on: the condition for (n, m) implies it for every prefix (n' <= n, m' <= m)
+    assert _prefix_condition(ordered[:128], 32) and _prefix_condition(ordered[:32], 8)
+
+
 def test_image_prep_restatement_matches_the_synthetic_loader():
     """oracle.image_prep (numpy float64, lib/datasets/kitti_dataset.py:44-55) == scenes.host_image_prep (torch float64): the two
     independent restatements of the reference's host-side preparation agree bit for bit, ragged sizes zero-padded."""
